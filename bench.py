@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""bench.py -- finitediffx_b200 headline benchmark (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one synthetic grid.  Headline workload (N=1):
+fdx.laplacian on a 512^3 fp32 grid, accuracy=4, central (BASELINE config 3, the configuration the
+north-star target is quoted on).  With N>1 the global grid is (512*N, 512, 512), slab-decomposed
+along axis 0 with NCCL halo exchange: per-GPU work is fixed ("weak" scaling).
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "laplacian_gpts_per_s"
+UNIT = "Gpts/s"
+
+WORKLOADS = {
+    # name: (op, spatial shape, n_in fields, n_out fields, dtype, accuracy, bytes per point)
+    "laplacian_512_f32_a4": dict(op="laplacian", n=512, dtype="f32", accuracy=4, fields_in=1, fields_out=1),
+    "divergence_512_f32_a4": dict(op="divergence", n=512, dtype="f32", accuracy=4, fields_in=3, fields_out=1),
+    "gradient_512_f32_a4": dict(op="gradient", n=512, dtype="f32", accuracy=4, fields_in=1, fields_out=3),
+    "curl_512_f32_a4": dict(op="curl", n=512, dtype="f32", accuracy=4, fields_in=3, fields_out=3),
+    "laplacian_512_f64_a8": dict(op="laplacian", n=512, dtype="f64", accuracy=8, fields_in=1, fields_out=1),
+    "laplacian_1024_f32_a4": dict(op="laplacian", n=1024, dtype="f32", accuracy=4, fields_in=1, fields_out=1),
+}
+HEADLINE = "laplacian_512_f32_a4"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Polls NVML for SM clock and throttle reasons DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {
+            "sm_mhz": float(np.median(self.samples)),
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def _bytes_per_point(w):
+    s = 4 if w["dtype"] == "f32" else 8
+    return s * (w["fields_in"] + w["fields_out"])
+
+
+def _make_input(w, device, seed, n0=None):
+    import torch
+
+    n = w["n"]
+    n0 = n if n0 is None else n0
+    dt = torch.float32 if w["dtype"] == "f32" else torch.float64
+    g = torch.Generator(device=device).manual_seed(seed)
+    shape = (n0, n, n) if w["fields_in"] == 1 else (w["fields_in"], n0, n, n)
+    return torch.randn(shape, generator=g, device=device, dtype=dt)
+
+
+def _call(fdx, w, x):
+    h = 1.0 / (w["n"] - 1)
+    if w["op"] == "divergence":
+        return fdx.divergence(x, accuracy=w["accuracy"], step_size=h, keepdims=False)
+    return getattr(fdx, w["op"])(x, accuracy=w["accuracy"], step_size=h)
+
+
+def _time_device(fn, inputs, steps, warmup, sampler=None, barrier=None):
+    """W warm-up + K timed steps, CUDA events on the launching (current) stream."""
+    import torch
+
+    for i in range(warmup):
+        fn(inputs[i % len(inputs)])
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx = sampler if sampler is not None else _Null()
+    with ctx:
+        e0.record()
+        for i in range(steps):
+            fn(inputs[i % len(inputs)])
+        e1.record()
+        torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return e0.elapsed_time(e1) / 1e3  # seconds
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+# ------------------------------------------------------------------------------ CPU arms
+def _cpu_threads():
+    import torch
+
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
+def _cpu_step(w, n):
+    """One CPU step of workload `w` on an n^3 sample (restated reference graph on torch-CPU)."""
+    import torch
+
+    from oracle import fdx_oracle_torch as OT
+
+    dt = torch.float32 if w["dtype"] == "f32" else torch.float64
+    g = torch.Generator().manual_seed(0)
+    shape = (n, n, n) if w["fields_in"] == 1 else (w["fields_in"], n, n, n)
+    x = torch.randn(shape, generator=g, dtype=dt)
+    h = 1.0 / (w["n"] - 1)
+
+    def step():
+        if w["op"] == "divergence":
+            return OT.divergence(x, accuracy=w["accuracy"], step_size=h, keepdims=False)
+        if w["op"] == "curl":
+            raise NotImplementedError
+        return getattr(OT, w["op"])(x, accuracy=w["accuracy"], step_size=h)
+
+    return step
+
+
+def _cpu_baseline(w, budget_s=12.0):
+    cores = _cpu_threads()
+    n = 256 if w["n"] >= 256 else w["n"]
+    step = _cpu_step(w, n)
+    step()  # warm-up
+    t0, reps = time.perf_counter(), 0
+    while True:
+        step()
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or reps >= 50:
+            break
+    gpts = n**3 * reps / el / 1e9
+    return {
+        "value": gpts,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{w['op']} on a {n}^3 {w['dtype']} sub-grid of the workload, {reps} reps in {el:.1f}s; restated reference algorithm on torch-CPU, not jax[cpu] (jax is not installed)",
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (torch-CPU restatement)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = WORKLOADS[args.workload]
+    cores = _cpu_threads()
+    # size the per-step sample so that (K+W) steps end within ~2 minutes
+    n = 128
+    step = _cpu_step(w, n)
+    step()
+    t0 = time.perf_counter()
+    step()
+    t1 = time.perf_counter() - t0
+    best = n
+    for cand in (256, 512):
+        if cand <= w["n"] and t1 * (cand / n) ** 3 * (args.steps + args.warmup) <= 120.0:
+            best = cand
+        else:
+            break
+    if best != n:
+        n = best
+        step = _cpu_step(w, n)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = n**3 * args.steps / el / 1e9
+    sample = f"{w['op']} on a {n}^3 {w['dtype']} sub-grid per step; restated reference algorithm on torch-CPU, {cores} threads, not jax[cpu]"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": w["dtype"],
+        "data": "synthetic",
+        "config": {"workload": args.workload, "grid": [w["n"]] * 3, "accuracy": w["accuracy"], "method": "central"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+
+    import finitediffx_b200 as fdx
+    from finitediffx_b200 import _cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    n = w["n"]
+    pts_per_gpu = n**3
+    _cabi.load()
+
+    barrier = (lambda: dist.barrier()) if dist else None
+    if world == 1:
+        # rotate over 3 input buffers so nothing stays L2-resident between steps (inputs >> L2)
+        inputs = [_make_input(w, dev, seed=s) for s in range(3)]
+        fn = lambda x: _call(fdx, w, x)
+    else:
+        from finitediffx_b200 import distributed as fd
+
+        slab = fd.Slab(global_n0=n * world, rank=rank, world=world, group=dist.group.WORLD)
+        h = 1.0 / (n - 1)
+        op = fd.SlabOperator(slab, w["op"], spatial=(n, n, n), dtype=torch.float32 if w["dtype"] == "f32" else torch.float64, accuracy=w["accuracy"], step_size=h, device=dev, n_buffers=3)
+        inputs = list(range(3))
+        for b in inputs:
+            op.fill_random(b, seed=100 * rank + b)
+        fn = lambda b: op.step(b)
+
+    launches0 = _cabi.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # count launches over the timed region only
+    for i in range(args.warmup):
+        fn(inputs[i % len(inputs)])
+    torch.cuda.synchronize()
+    launches0 = _cabi.launch_count()
+    secs = _time_device(fn, inputs, args.steps, 0, sampler=sampler, barrier=barrier)
+    launches = _cabi.launch_count() - launches0
+    if dist:
+        t = torch.tensor([secs], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    value = pts_per_gpu * world * args.steps / secs / 1e9
+    ms = secs / args.steps * 1e3
+
+    # ---- end-to-end through the public API with HOST buffers (H2D + kernel + D2H every step)
+    e2e = None
+    if world == 1:
+        hx = [torch.empty(inputs[0].shape, dtype=inputs[0].dtype, pin_memory=True).copy_(inputs[i]) for i in range(2)]
+        e_steps = max(3, min(args.steps, 10))
+        for i in range(2):
+            _call(fdx, w, hx[i % 2])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e_steps):
+            r = _call(fdx, w, hx[i % 2])
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        assert not r.is_cuda
+        e2e = {
+            "value": pts_per_gpu * e_steps / el / 1e9,
+            "unit": UNIT,
+            "h2d_bytes_per_step": int(hx[0].numel() * hx[0].element_size()),
+            "d2h_bytes_per_step": int(r.numel() * r.element_size()),
+            "steps": e_steps,
+            "api": f"finitediffx_b200.{w['op']}(pinned host tensor) -> host tensor",
+        }
+    else:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "slab data is device-resident at N>1; e2e is measured at N=1"}
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = _peaks()
+    alg_bytes = _bytes_per_point(w) * pts_per_gpu
+    achieved = alg_bytes / (secs / args.steps) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": w["dtype"],
+        "data": "synthetic",
+        "config": {
+            "workload": args.workload,
+            "grid": [n * world, n, n],
+            "grid_per_gpu": [n, n, n],
+            "accuracy": w["accuracy"],
+            "method": "central",
+            "step_size": f"1/{n - 1}",
+            "decomposition": "single GPU" if world == 1 else f"slab along axis 0, {world} ranks, NCCL halo exchange",
+            "l2": "3 rotating inputs, each larger than L2 (126 MB); outputs freshly written",
+        },
+        "clocks": sampler.summary() if sampler else None,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "kernel": _cabi.last_kernel(),
+        "roofline": {
+            "bound": "hbm",
+            "achieved": achieved,
+            "peak": peak,
+            "unit": "GB/s",
+            "frac": achieved / peak,
+            "frac_of_8TBs_nominal": achieved / 8000.0,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "traffic": traffic,
+        },
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = _cpu_baseline(w)
+    if world == 1 and args.extras:
+        extras = {}
+        for name in ("divergence_512_f32_a4", "gradient_512_f32_a4", "curl_512_f32_a4", "laplacian_512_f64_a8"):
+            if name == args.workload:
+                continue
+            we = WORKLOADS[name]
+            del inputs
+            torch.cuda.empty_cache()
+            inputs = [_make_input(we, dev, seed=s) for s in range(2)]
+            s = _time_device(lambda x: _call(fdx, we, x), inputs, 20, 5)
+            ach = _bytes_per_point(we) * we["n"] ** 3 / (s / 20) / 1e9
+            extras[name] = {"gpts_per_s": we["n"] ** 3 * 20 / s / 1e9, "ms": s / 20 * 1e3, "hbm_gbs": ach, "frac": ach / peak, "kernel": _cabi.last_kernel()}
+        # laplacian forward + vjp (jax.grad through the custom_vjp analogue)
+        del inputs
+        torch.cuda.empty_cache()
+        x = _make_input(w, dev, seed=0).requires_grad_(True)
+        gcot = _make_input(w, dev, seed=1)
+
+        def fwd_bwd(_):
+            out = _call(fdx, w, x)
+            (gx,) = torch.autograd.grad(out, x, gcot)
+            return gx
+
+        s = _time_device(fwd_bwd, [0], 20, 5)
+        extras["laplacian_512_f32_a4_fwd_plus_vjp"] = {"gpts_per_s": n**3 * 20 / s / 1e9, "ms": s / 20 * 1e3}
+        line["extras"] = extras
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
+    ap.add_argument("--extras", action="store_true", help="also time the other fused operators (N=1)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

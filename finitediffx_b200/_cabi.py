@@ -1,0 +1,252 @@
+"""ctypes binding of libfdx_b200.so (the C ABI declared in include/fdx_b200.h).
+
+This is the testable stand-in for the ``jax.ffi`` registration the north star names (JAX is not
+installed in this image; INTEGRATION.md shows the XLA-FFI shim over the same symbols).  It only
+marshals raw device pointers, sizes and the current CUDA stream: torch is used for device memory
+and streams, nothing else.
+
+There is no CPU fallback: if the shared library is missing, ``load()`` raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from .plan import MAX_TAPS, AxisPlan
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libfdx_b200.so")
+_lib = None
+_lock = threading.Lock()
+
+MAX_BAND = 64  # FDX_MAX_BAND
+
+
+class FdxError(RuntimeError):
+    pass
+
+
+class _AxisDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("lo", C.c_int32),
+        ("hi", C.c_int32),
+        ("main_taps", C.c_double * MAX_TAPS),
+        ("nl", C.c_int32),
+        ("wl", C.c_int32),
+        ("nr", C.c_int32),
+        ("wr", C.c_int32),
+        ("band_l", C.POINTER(C.c_double)),
+        ("band_r", C.POINTER(C.c_double)),
+    ]
+
+
+class Slab(C.Structure):
+    _fields_ = [("z_begin", C.c_int32), ("z_end", C.c_int32), ("halo_lo", C.c_int32), ("halo_hi", C.c_int32)]
+
+
+EXPORTS = (
+    "fdx_plan_create",
+    "fdx_plan_destroy",
+    "fdx_axis_apply_f32",
+    "fdx_axis_apply_f64",
+    "fdx_laplacian3d_f32",
+    "fdx_laplacian3d_f64",
+    "fdx_divergence3d_f32",
+    "fdx_divergence3d_f64",
+    "fdx_gradient3d_f32",
+    "fdx_gradient3d_f64",
+    "fdx_curl3d_f32",
+    "fdx_curl3d_f64",
+    "fdx_version",
+    "fdx_error_string",
+    "fdx_launch_count",
+    "fdx_last_kernel",
+)
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load libfdx_b200.so; raise loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise FdxError(
+                f"{_LIB_PATH} is missing: the CUDA library has not been built. Run "
+                "`python -m finitediffx_b200._build` (needs nvcc). There is no CPU fallback."
+            )
+        lib = C.CDLL(_LIB_PATH)
+        vp, i64, dbl, i32 = C.c_void_p, C.c_int64, C.c_double, C.c_int
+        lib.fdx_plan_create.argtypes = [C.POINTER(vp), C.POINTER(_AxisDesc)]
+        lib.fdx_plan_destroy.argtypes = [vp]
+        for sfx in ("f32", "f64"):
+            getattr(lib, f"fdx_axis_apply_{sfx}").argtypes = [vp, vp, vp, i64, i64, dbl, i32, vp]
+            getattr(lib, f"fdx_laplacian3d_{sfx}").argtypes = [C.POINTER(vp), vp, vp, C.POINTER(dbl), C.POINTER(Slab), vp]
+            getattr(lib, f"fdx_divergence3d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(dbl), C.POINTER(Slab), vp]
+            getattr(lib, f"fdx_gradient3d_{sfx}").argtypes = [C.POINTER(vp), vp, C.POINTER(vp), C.POINTER(dbl), C.POINTER(Slab), vp]
+            getattr(lib, f"fdx_curl3d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(dbl), C.POINTER(Slab), vp]
+        lib.fdx_error_string.restype = C.c_char_p
+        lib.fdx_error_string.argtypes = [i32]
+        lib.fdx_launch_count.restype = i64
+        lib.fdx_last_kernel.restype = C.c_char_p
+        for name in EXPORTS:
+            getattr(lib, name)  # AttributeError here means header and library disagree
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str = "fdx call"):
+    if code != 0:
+        msg = load().fdx_error_string(code).decode()
+        raise FdxError(f"{what} failed with code {code}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().fdx_launch_count())
+
+
+def last_kernel() -> str:
+    return load().fdx_last_kernel().decode()
+
+
+# ------------------------------------------------------------------------------ device plans
+class DevicePlan:
+    """Device-resident plan handle (fdx_plan_t) built from a host AxisPlan."""
+
+    def __init__(self, plan: AxisPlan, device: torch.device):
+        if plan.taps > MAX_TAPS:
+            raise FdxError(f"{plan.taps} taps exceed FDX_MAX_TAPS={MAX_TAPS}")
+        self.host = plan
+        self.device = device
+        desc = _AxisDesc()
+        desc.n, desc.lo, desc.hi = plan.n, plan.lo, plan.hi
+        for k in range(MAX_TAPS):
+            desc.main_taps[k] = float(plan.main[k]) if k < plan.taps else 0.0
+        desc.nl, desc.wl, desc.nr, desc.wr = plan.nl, plan.wl, plan.nr, plan.wr
+        self._bl = np.ascontiguousarray(plan.band_l, dtype=np.float64)
+        self._br = np.ascontiguousarray(plan.band_r, dtype=np.float64)
+        desc.band_l = self._bl.ctypes.data_as(C.POINTER(C.c_double)) if self._bl.size else None
+        desc.band_r = self._br.ctypes.data_as(C.POINTER(C.c_double)) if self._br.size else None
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            check(load().fdx_plan_create(C.byref(handle), C.byref(desc)), "fdx_plan_create")
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and _lib is not None:
+                _lib.fdx_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_plan_cache: dict = {}
+
+
+def device_plan(plan: AxisPlan, device: torch.device) -> DevicePlan:
+    """The coefficient/plan cache: one device plan per (host plan, device)."""
+    key = (id(plan), device.index if device.index is not None else torch.cuda.current_device())
+    hit = _plan_cache.get(key)
+    if hit is None or hit.host is not plan:
+        hit = DevicePlan(plan, device)
+        _plan_cache[key] = hit
+    return hit
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _sfx(t: torch.Tensor) -> str:
+    if t.dtype == torch.float32:
+        return "f32"
+    if t.dtype == torch.float64:
+        return "f64"
+    raise FdxError(f"unsupported dtype {t.dtype}")
+
+
+def _require(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise FdxError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise FdxError(f"{name} must be contiguous")
+
+
+def axis_apply(plan: AxisPlan, x: torch.Tensor, out: torch.Tensor, axis: int, alpha: float, accumulate: bool = False):
+    """out (+)= alpha * D_axis x for contiguous CUDA tensors of identical shape."""
+    _require(x, "x")
+    _require(out, "out")
+    assert x.shape == out.shape and x.dtype == out.dtype
+    if x.numel() == 0:
+        return
+    shape = x.shape
+    assert shape[axis] == plan.n, (shape, axis, plan.n)
+    outer = int(np.prod(shape[:axis], dtype=np.int64)) if axis > 0 else 1
+    inner = int(np.prod(shape[axis + 1 :], dtype=np.int64)) if axis + 1 < len(shape) else 1
+    dp = device_plan(plan, x.device)
+    with torch.cuda.device(x.device):
+        fn = getattr(load(), f"fdx_axis_apply_{_sfx(x)}")
+        check(
+            fn(dp.handle, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), outer, inner, float(alpha), int(bool(accumulate)), _stream_ptr(x.device)),
+            "fdx_axis_apply",
+        )
+
+
+def _handles(plans: Sequence[AxisPlan], device):
+    dps = [device_plan(p, device) for p in plans]
+    arr = (C.c_void_p * 3)(*[dp.handle for dp in dps])
+    return dps, arr
+
+
+def _ptrs(tensors: Sequence[torch.Tensor]):
+    return (C.c_void_p * 3)(*[C.c_void_p(t.data_ptr()) for t in tensors])
+
+
+def _alphas(alpha: Sequence[float]):
+    return (C.c_double * 3)(*[float(a) for a in alpha])
+
+
+def _slab(slab):
+    return C.byref(slab) if slab is not None else None
+
+
+def fused3d(kind: str, plans: Sequence[AxisPlan], xs, outs, alpha: Sequence[float], slab: "Slab | None" = None) -> int:
+    """Call one of the fused 3-D entry points.  ``xs`` / ``outs`` are a tensor (scalar field) or a
+    sequence of three tensors (vector field components).  Returns the library's status code for
+    FDX_EUNSUPPORTED so callers can fall back to ``axis_apply``; raises on any other error."""
+    first = xs if isinstance(xs, torch.Tensor) else xs[0]
+    dev = first.device
+    for t in ([xs] if isinstance(xs, torch.Tensor) else list(xs)) + ([outs] if isinstance(outs, torch.Tensor) else list(outs)):
+        _require(t, "tensor")
+    keep, hp = _handles(plans, dev)
+    sfx = _sfx(first)
+    st = _stream_ptr(dev)
+    lib = load()
+    with torch.cuda.device(dev):
+        if kind == "laplacian":
+            rc = getattr(lib, f"fdx_laplacian3d_{sfx}")(hp, C.c_void_p(xs.data_ptr()), C.c_void_p(outs.data_ptr()), _alphas(alpha), _slab(slab), st)
+        elif kind == "divergence":
+            rc = getattr(lib, f"fdx_divergence3d_{sfx}")(hp, _ptrs(xs), C.c_void_p(outs.data_ptr()), _alphas(alpha), _slab(slab), st)
+        elif kind == "gradient":
+            rc = getattr(lib, f"fdx_gradient3d_{sfx}")(hp, C.c_void_p(xs.data_ptr()), _ptrs(outs), _alphas(alpha), _slab(slab), st)
+        elif kind == "curl":
+            rc = getattr(lib, f"fdx_curl3d_{sfx}")(hp, _ptrs(xs), _ptrs(outs), _alphas(alpha), _slab(slab), st)
+        else:
+            raise ValueError(kind)
+    del keep
+    if rc == -2:  # FDX_EUNSUPPORTED
+        return rc
+    check(rc, f"fdx_{kind}3d")
+    return 0

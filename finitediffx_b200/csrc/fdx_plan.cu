@@ -1,0 +1,82 @@
+// Plan lifetime and library introspection (include/fdx_b200.h).
+//
+// A plan is the device-resident form of one axis operator.  It plays the role of the reference's
+// only cache -- the jax.jit cache around the coefficient solve, finitediffx/_src/utils.py:100 --
+// except that the coefficients arrive already solved (exactly, in float64) from the host.
+#include <atomic>
+#include <cstring>
+#include <new>
+
+#include "fdx_common.cuh"
+
+namespace fdx {
+thread_local const char* g_last_kernel = "";
+static std::atomic<int64_t> g_launches{0};
+void count_launch(const char* family, int launches) {
+  g_last_kernel = family;
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
+}
+}  // namespace fdx
+
+extern "C" int fdx_plan_create(fdx_plan_t* plan, const fdx_axis_desc* d) {
+  if (!plan || !d) return FDX_EINVAL;
+  *plan = nullptr;
+  const int taps = d->hi - d->lo + 1;
+  if (d->n < 0 || taps < 1 || taps > FDX_MAX_TAPS) return FDX_EINVAL;
+  if (d->nl < 0 || d->nr < 0 || d->wl < 0 || d->wr < 0) return FDX_EINVAL;
+  if (d->nl + d->nr > d->n || d->wl > d->n || d->wr > d->n) return FDX_EINVAL;
+  if ((d->nl > 0 && (!d->band_l || d->wl == 0)) || (d->nr > 0 && (!d->band_r || d->wr == 0))) return FDX_EINVAL;
+  // main rows must be able to reach all their taps unless the caller supplies halos (slab plans
+  // with nl == 0 / nr == 0 read the halo planes instead; the fused entry points check that).
+  if (d->nl > 0 && d->nl < -d->lo) return FDX_EINVAL;
+  if (d->nr > 0 && d->nr < d->hi) return FDX_EINVAL;
+
+  fdx_plan_s* p = new (std::nothrow) fdx_plan_s();
+  if (!p) return (int)cudaErrorMemoryAllocation;
+  p->n = d->n, p->lo = d->lo, p->hi = d->hi;
+  p->nl = d->nl, p->wl = d->wl, p->nr = d->nr, p->wr = d->wr;
+  std::memcpy(p->main_taps, d->main_taps, sizeof(p->main_taps));
+  p->band_l = p->band_r = nullptr;
+  cudaError_t e = cudaGetDevice(&p->device);
+  const size_t bl = sizeof(double) * (size_t)d->nl * d->wl, br = sizeof(double) * (size_t)d->nr * d->wr;
+  if (e == cudaSuccess && bl) e = cudaMalloc((void**)&p->band_l, bl);
+  if (e == cudaSuccess && bl) e = cudaMemcpy(p->band_l, d->band_l, bl, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && br) e = cudaMalloc((void**)&p->band_r, br);
+  if (e == cudaSuccess && br) e = cudaMemcpy(p->band_r, d->band_r, br, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(p->band_l);
+    cudaFree(p->band_r);
+    delete p;
+    return (int)e;
+  }
+  *plan = p;
+  return FDX_OK;
+}
+
+extern "C" int fdx_plan_destroy(fdx_plan_t plan) {
+  if (!plan) return FDX_OK;
+  cudaFree(plan->band_l);
+  cudaFree(plan->band_r);
+  delete plan;
+  return FDX_OK;
+}
+
+extern "C" int fdx_version(void) { return 1000 * 0 + 1; }
+
+extern "C" const char* fdx_error_string(int code) {
+  switch (code) {
+    case FDX_OK:
+      return "ok";
+    case FDX_EINVAL:
+      return "fdx: invalid argument";
+    case FDX_EUNSUPPORTED:
+      return "fdx: unsupported shape/plan combination for this entry point";
+    case FDX_EALIGN:
+      return "fdx: pointer not aligned to its element size";
+    default:
+      return code > 0 ? cudaGetErrorString((cudaError_t)code) : "fdx: unknown error";
+  }
+}
+
+extern "C" int64_t fdx_launch_count(void) { return fdx::g_launches.load(std::memory_order_relaxed); }
+extern "C" const char* fdx_last_kernel(void) { return fdx::g_last_kernel; }

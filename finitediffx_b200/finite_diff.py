@@ -1,0 +1,332 @@
+"""Array finite-difference operators: drop-in for ``finitediffx/_src/finite_diff.py``.
+
+Same names, keyword-only signatures, defaults and error behaviour as the reference
+(``difference`` :168-297, ``gradient`` :300-351, ``jacobian`` :354-401, ``divergence`` :404-457,
+``hessian`` :460-529, ``laplacian`` :532-575, ``curl`` :671-741); the arithmetic runs in the
+hand-written CUDA library behind include/fdx_b200.h.
+
+Every operator is a short list of *terms* ``out[co] += alpha * D(axis, derivative, accuracy,
+method) in[ci]``; ``_StencilOp`` executes a term list, picking the fused single-pass 3-D kernels
+when the list is a laplacian / divergence / gradient / curl on a 3-D grid and the generic axis
+kernels (accumulating in place, no temporaries, no stack copy) otherwise.  Its backward pass
+executes the transposed term list with transposed plans -- boundary rows included -- which is what
+``jax.grad`` through the reference computes; it is the
+``torch.autograd.Function`` analogue of the ``jax.custom_vjp`` the north star asks for.
+
+Arrays: CUDA ``torch.Tensor`` in -> CUDA tensor out.  Host data (NumPy arrays, lists, CPU tensors)
+is copied to the current CUDA device, processed there, and returned in the kind it came in.
+"""
+
+from __future__ import annotations
+
+import dataclasses as dc
+from itertools import combinations
+from typing import Literal, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .plan import AxisPlan, axis_plan, axis_plan_t
+from .utils import _check_and_return
+
+__all__ = ("hessian", "difference", "gradient", "jacobian", "laplacian", "curl", "divergence")
+
+MethodKind = Literal["central", "forward", "backward"]
+
+
+# ------------------------------------------------------------------------------- term lists
+@dc.dataclass(frozen=True)
+class Term:
+    co: int  # output field index
+    ci: int  # input field index
+    axis: int  # spatial axis
+    derivative: int
+    accuracy: int
+    method: str
+    alpha: float  # runtime scale, 1 / step**derivative (with sign)
+    transposed: bool = False
+
+    def plan(self, n: int) -> AxisPlan:
+        if self.transposed:
+            return axis_plan_t(n, self.derivative, self.accuracy, self.method)
+        return axis_plan(n, self.derivative, self.accuracy, self.method, self.axis)
+
+    def t(self) -> "Term":
+        return dc.replace(self, co=self.ci, ci=self.co, transposed=not self.transposed)
+
+
+def _match_fused(terms: Sequence[Term], n_in: int, n_out: int, spatial):
+    """Recognise the four fused 3-D shapes.  Returns (kind, per-axis terms) or None."""
+    if len(spatial) != 3 or not terms:
+        return None
+    t0 = terms[0]
+    if any((t.derivative, t.accuracy, t.method, t.transposed) != (t0.derivative, t0.accuracy, t0.method, t0.transposed) for t in terms):
+        return None
+    by = {(t.co, t.ci, t.axis): t for t in terms}
+    if len(by) != len(terms):
+        return None
+    if len(terms) == 3:
+        if n_in == 1 and n_out == 1 and set(by) == {(0, 0, k) for k in range(3)}:
+            return "laplacian", [by[(0, 0, k)] for k in range(3)]
+        if n_out == 1 and n_in >= 3 and set(by) == {(0, k, k) for k in range(3)}:
+            return "divergence", [by[(0, k, k)] for k in range(3)]
+        if n_in == 1 and n_out >= 3 and set(by) == {(k, 0, k) for k in range(3)}:
+            return "gradient", [by[(k, 0, k)] for k in range(3)]
+    if len(terms) == 6 and n_in == 3 and n_out == 3:
+        # out_0 = a1 D1 x2 - a2 D2 x1 ; out_1 = a2 D2 x0 - a0 D0 x2 ; out_2 = a0 D0 x1 - a1 D1 x0
+        plus = {(0, 2, 1), (1, 0, 2), (2, 1, 0)}
+        minus = {(0, 1, 2), (1, 2, 0), (2, 0, 1)}
+        if set(by) == plus | minus:
+            axis_terms = []
+            for k in range(3):
+                tp = next(by[key] for key in plus if key[2] == k)
+                tm = next(by[key] for key in minus if key[2] == k)
+                if tp.alpha != -tm.alpha:
+                    return None
+                axis_terms.append(tp)
+            return "curl", axis_terms
+    return None
+
+
+def _execute(terms: Sequence[Term], x: torch.Tensor, n_out: int) -> torch.Tensor:
+    """x: (n_in, *spatial) contiguous CUDA tensor -> (n_out, *spatial)."""
+    n_in, spatial = x.shape[0], tuple(x.shape[1:])
+    out = torch.empty((n_out,) + spatial, dtype=x.dtype, device=x.device)
+    if x.numel() == 0:
+        return out
+    fused = _match_fused(terms, n_in, n_out, spatial)
+    if fused is not None:
+        kind, axis_terms = fused
+        plans = [t.plan(spatial[k]) for k, t in enumerate(axis_terms)]
+        alpha = [t.alpha for t in axis_terms]
+        xs = x[0] if kind in ("laplacian", "gradient") else [x[0], x[1], x[2]]
+        outs = out[0] if kind in ("laplacian", "divergence") else [out[0], out[1], out[2]]
+        if _cabi.fused3d(kind, plans, xs, outs, alpha) == 0:
+            if n_out > 3 and kind == "gradient":
+                out[3:].zero_()
+            return out
+    written = [False] * n_out
+    for t in terms:
+        _cabi.axis_apply(t.plan(spatial[t.axis]), x[t.ci], out[t.co], t.axis, t.alpha, accumulate=written[t.co])
+        written[t.co] = True
+    for co, w in enumerate(written):
+        if not w:
+            out[co].zero_()
+    return out
+
+
+class _StencilOp(torch.autograd.Function):
+    """Linear stencil operator given by a term list; backward = transposed term list."""
+
+    @staticmethod
+    def forward(ctx, x, terms, n_out):
+        ctx.terms, ctx.n_in = terms, x.shape[0]
+        return _execute(terms, x, n_out)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        terms_t = tuple(t.t() for t in ctx.terms)
+        return _StencilOp.apply(g, terms_t, ctx.n_in), None, None
+
+
+# ------------------------------------------------------------------------ array marshalling
+def _to_device(array):
+    """-> (contiguous CUDA tensor of float32/float64, restore(result) -> caller's array kind)."""
+    if isinstance(array, torch.Tensor):
+        t, kind = array, ("cuda" if array.is_cuda else "cpu")
+    else:
+        a = np.asarray(array)
+        if a.dtype == object:
+            raise TypeError(f"cannot interpret {type(array)} as a numeric array")
+        t, kind = torch.from_numpy(np.ascontiguousarray(a)), "numpy"
+    if not torch.cuda.is_available():
+        raise _cabi.FdxError("finitediffx_b200 needs a CUDA device (B200); there is no CPU fallback")
+    _cabi.load()
+    # output dtype rule (reference: promote(coefficients, input)): float64 stays float64,
+    # everything else (float32, half, bfloat16, integers, bool) computes in float32
+    target = torch.float64 if t.dtype == torch.float64 else torch.float32
+    src_device = t.device
+    if not t.is_cuda:
+        t = t.to("cuda", non_blocking=False)
+    t = t.to(target).contiguous()
+
+    def restore(r: torch.Tensor):
+        if kind == "cuda":
+            return r
+        if kind == "cpu":
+            return r.to(src_device)
+        return r.cpu().numpy()
+
+    return t, restore
+
+
+def _alpha(step, derivative: int) -> float:
+    if isinstance(step, torch.Tensor):
+        step = step.item()
+    return 1.0 / (float(step) ** derivative)
+
+
+def _norm_axis(axis: int, ndim: int) -> int:
+    if not -ndim <= axis < ndim:
+        raise ValueError(f"axis {axis} is out of bounds for array of dimension {ndim}")
+    return axis % ndim
+
+
+def _run(x_fields: torch.Tensor, terms, n_out: int) -> torch.Tensor:
+    terms = tuple(terms)
+    for t in terms:  # validate sizes/methods up front so errors match the reference's ValueError
+        t.plan(x_fields.shape[1 + t.axis])
+    return _StencilOp.apply(x_fields, terms, n_out)
+
+
+# --------------------------------------------------------------------------------- operators
+def difference(
+    array,
+    *,
+    axis: int = 0,
+    accuracy: int = 1,
+    step_size=1.0,
+    derivative: int = 1,
+    method: MethodKind = "central",
+):
+    """Compute the finite difference derivative along a given axis with a given accuracy
+    using central difference for interior points and forward/backward difference for boundary points
+
+    Args:
+        array: input array
+        axis: axis along which to compute the gradient. Default is 0
+        accuracy: accuracy order of the gradient. Default is 1
+        step_size: step size. Default is 1
+        derivative: derivative order of the gradient. Default is 1
+        method: the method to use (forward, central, backward). Default is central
+    Returns:
+        Finite difference derivative along the given axis
+
+    Drop-in for the reference's ``difference`` (finite_diff.py:168-297); raises ``ValueError`` when
+    the axis is too short for the stencil or the method is unknown (:292-297).
+    """
+    x, restore = _to_device(array)
+    if x.ndim == 0:
+        raise ValueError("difference needs an array with at least one axis")
+    ax = _norm_axis(axis, x.ndim)
+    term = Term(0, 0, ax, int(derivative), int(accuracy), method, _alpha(step_size, derivative))
+    return restore(_run(x.unsqueeze(0), [term], 1)[0])
+
+
+def gradient(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
+    """Compute the ∇F of input array where F is a scalar function of x and
+    returns vectors of the same shape as x stacked along the first axis.
+
+    Drop-in for the reference's ``gradient`` (finite_diff.py:300-351).  Index notation: dF/dxi
+    """
+    x, restore = _to_device(array)
+    accuracy = _check_and_return(accuracy, x.ndim, "accuracy")
+    step_size = _check_and_return(step_size, x.ndim, "step_size")
+    terms = [Term(k, 0, k, 1, int(a), method, _alpha(h, 1)) for k, (a, h) in enumerate(zip(accuracy, step_size))]
+    return restore(_run(x.unsqueeze(0), terms, x.ndim))
+
+
+def jacobian(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
+    """Compute the ∂Fi/∂xj of input array where F is a vector function of x (leading axis).
+
+    Drop-in for the reference's ``jacobian`` (finite_diff.py:354-401): output (C, ndim-1, *spatial).
+    """
+    x, restore = _to_device(array)
+    nd = x.ndim - 1
+    accuracy = _check_and_return(accuracy, nd, "accuracy")
+    step_size = _check_and_return(step_size, nd, "step_size")
+    ncomp = x.shape[0]
+    terms = [
+        Term(c * nd + k, c, k, 1, int(a), method, _alpha(h, 1))
+        for c in range(ncomp)
+        for k, (a, h) in enumerate(zip(accuracy, step_size))
+    ]
+    out = _run(x, terms, ncomp * nd)
+    return restore(out.reshape((ncomp, nd) + tuple(x.shape[1:])))
+
+
+def divergence(array, *, accuracy=1, step_size=1, keepdims: bool = True, method: MethodKind = "central"):
+    """Compute the ∇.F of input array where F is a vector field whose components
+    are the first axis of x and returns a scalar field
+
+    Drop-in for the reference's ``divergence`` (finite_diff.py:404-457).  Index notation: dFi/dxi
+    """
+    x, restore = _to_device(array)
+    nd = x.ndim - 1
+    accuracy = _check_and_return(accuracy, nd, "accuracy")
+    step_size = _check_and_return(step_size, nd, "step_size")
+    # zip() in the reference stops at ndim-1 axes: extra leading components are ignored
+    terms = [Term(0, k, k, 1, int(a), method, _alpha(h, 1)) for k, (a, h) in enumerate(zip(accuracy, step_size))]
+    if x.shape[0] < nd:
+        raise IndexError(f"index {x.shape[0]} is out of bounds for axis 0 with size {x.shape[0]}")
+    out = _run(x, terms, 1)
+    return restore(out if keepdims else out[0])
+
+
+def hessian(array, *, accuracy=2, step_size=1, method: MethodKind = "central"):
+    """Compute hessian of F: R^m -> R.  Index notation: d2F/dxij
+
+    Drop-in for the reference's ``hessian`` (finite_diff.py:460-529), including its indexing
+    ``H[i][j] = F[i + j]`` (:499,510,524-529), which for ndim >= 3 makes key 2 both d2/dx1^2 and
+    d2/dx0dx2: results are bug-compatible with the reference.  Off-diagonal
+    entries are ``difference(difference(x, ax1), ax2)`` so boundary rows compose as they do there.
+    """
+    x, restore = _to_device(array)
+    nd = x.ndim
+    accuracy = _check_and_return(accuracy, nd, "accuracy")
+    step_size = _check_and_return(step_size, nd, "step_size")
+    xf = x.unsqueeze(0)
+    table = {}
+    for k in range(nd):
+        table[2 * k] = _run(xf, [Term(0, 0, k, 2, int(accuracy[k]), method, _alpha(step_size[k], 2))], 1)
+    for a1, a2 in combinations(range(nd), 2):
+        inner = _run(xf, [Term(0, 0, a1, 1, int(accuracy[a1]), method, _alpha(step_size[a1], 1))], 1)
+        table[a1 + a2] = _run(inner, [Term(0, 0, a2, 1, int(accuracy[a2]), method, _alpha(step_size[a2], 1))], 1)
+    rows = [torch.cat([table[i + j] for j in range(nd)], dim=0) for i in range(nd)]
+    return restore(torch.stack(rows, dim=0))
+
+
+def laplacian(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
+    """Compute the ΔF of input array.  Index notation: d2F/dxi2
+
+    Drop-in for the reference's ``laplacian`` (finite_diff.py:532-575).
+    """
+    x, restore = _to_device(array)
+    accuracy = _check_and_return(accuracy, x.ndim, "accuracy")
+    step_size = _check_and_return(step_size, x.ndim, "step_size")
+    terms = [Term(0, 0, k, 2, int(a), method, _alpha(h, 2)) for k, (a, h) in enumerate(zip(accuracy, step_size))]
+    return restore(_run(x.unsqueeze(0), terms, 1)[0])
+
+
+def curl(array, *, accuracy=1, step_size=1, method: MethodKind = "central", keepdims: bool = True):
+    """Compute the ∇×F of input array where F is a vector field whose components
+    are the first axis of x and returns a vector field.  Index notation: εijk dFk/dxj
+
+    Drop-in for the reference's ``curl`` (finite_diff.py:671-741): 3-D fields need shape (3, ...)
+    (``keepdims`` ignored, as there), 2-D fields shape (2, ...); anything else raises ``ValueError``.
+    """
+    x, restore = _to_device(array)
+    nd = x.ndim - 1
+    accuracy = _check_and_return(accuracy, nd, "accuracy")
+    step_size = _check_and_return(step_size, nd, "step_size")
+
+    def term(co, ci, ax, sign):
+        return Term(co, ci, ax, 1, int(accuracy[ax]), method, sign * _alpha(step_size[ax], 1))
+
+    if x.ndim == 4 and x.shape[0] == 3:
+        terms = [
+            term(0, 2, 1, +1), term(0, 1, 2, -1),
+            term(1, 0, 2, +1), term(1, 2, 0, -1),
+            term(2, 1, 0, +1), term(2, 0, 1, -1),
+        ]  # fmt: skip
+        return restore(_run(x, terms, 3))
+    if x.ndim == 3 and x.shape[0] == 2:
+        out = _run(x, [term(0, 1, 0, +1), term(0, 0, 1, -1)], 1)
+        return restore(out if keepdims else out[0])
+    raise ValueError(
+        f"`curl` is only implemented for 2D and 3D vector fields, got array.ndim={x.ndim}"
+        "for 2D vector fields, the leading axis must have a shape=2, "
+        "for 3D vector fields, the leading axis must have a shape=3"
+    )

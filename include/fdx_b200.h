@@ -1,0 +1,128 @@
+/*
+ * fdx_b200 -- C ABI of the B200-native finite-difference stencil library.
+ *
+ * The reference (ASEM000/finitediffX) has no native seam: its array path is pure Python on
+ * jax.numpy.  Every public operator funnels through `difference`
+ * (finitediffx/_src/finite_diff.py:168-297), so that is where this ABI cuts: one entry point
+ * for the 1-D axis operator, and one per fused vector-calculus operator.  A binding
+ * (ctypes here, jax.ffi / XLA custom call in INTEGRATION.md) only has to marshal raw device
+ * pointers, sizes and a stream.
+ *
+ * Conventions
+ *   - all array pointers are DEVICE pointers, C-contiguous, caller-owned, outputs pre-allocated,
+ *     inputs and outputs must not alias;
+ *   - `stream` is a cudaStream_t passed as void*; compute entry points only enqueue work:
+ *     no allocation, no synchronisation, re-entrant from any host thread;
+ *   - every function returns 0 on success, a negative FDX_E* code on misuse, or a positive
+ *     cudaError_t value; no exception crosses the ABI;
+ *   - `alpha` is the runtime scale (1 / step_size**derivative in the reference,
+ *     finite_diff.py:257,270,280,290); it is NOT part of a plan because `step_size` is a traced
+ *     value in the reference.
+ *
+ * A plan (fdx_plan_t) is the device-resident form of one 1-D operator: uniform "main" taps plus
+ * dense boundary bands (the reference's one-sided boundary stencils, finite_diff.py:75-88,
+ * 105-113, 130-138, 155-163, or their transposes for the adjoint).  It replaces the reference's
+ * only cache, the jax.jit cache around the coefficient solve (finitediffx/_src/utils.py:100).
+ */
+#ifndef FDX_B200_H_
+#define FDX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDX_MAX_TAPS 16
+#define FDX_MAX_BAND 64 /* max band rows / band columns per side */
+
+#define FDX_OK 0
+#define FDX_EINVAL (-1)      /* bad argument (null pointer, negative size, taps > FDX_MAX_TAPS ...) */
+#define FDX_EUNSUPPORTED (-2) /* shape/plan combination this entry point does not cover; use fdx_axis_apply */
+#define FDX_EALIGN (-3)       /* pointer not aligned to its element size */
+
+typedef struct fdx_plan_s* fdx_plan_t;
+
+/* Host-side description of one axis operator (see finitediffx_b200/plan.py):
+ *   out[i] = sum_k main[k] * x[i + lo + k]                    nl <= i < n - nr
+ *   out[i] = sum_c band_l[i*wl + c] * x[c]                    i < nl
+ *   out[i] = sum_c band_r[(i-(n-nr))*wr + c] * x[n - wr + c]  i >= n - nr
+ * Coefficients are unscaled float64 (solved exactly on the host; replaces utils.py:100-111). */
+typedef struct {
+  int32_t n;
+  int32_t lo, hi;
+  double main_taps[FDX_MAX_TAPS];
+  int32_t nl, wl, nr, wr;
+  const double* band_l; /* HOST pointer, nl*wl, row major (may be NULL when nl == 0) */
+  const double* band_r; /* HOST pointer, nr*wr, row major (may be NULL when nr == 0) */
+} fdx_axis_desc;
+
+/* Plan lifetime.  create/destroy allocate and copy (cudaMalloc + cudaMemcpy): call them outside
+ * the hot path and outside stream capture.  A plan is bound to the device current at creation. */
+int fdx_plan_create(fdx_plan_t* plan, const fdx_axis_desc* desc);
+int fdx_plan_destroy(fdx_plan_t plan);
+
+/* ---- 1-D axis operator: replaces `difference` (finite_diff.py:168-297) and, with a transposed
+ * plan, its adjoint.  The array is viewed as (outer, n, inner), n == plan n, inner contiguous.
+ *   out = alpha * D x            accumulate == 0
+ *   out = out + alpha * D x      accumulate != 0                                             */
+int fdx_axis_apply_f32(fdx_plan_t plan, const float* x, float* out, int64_t outer, int64_t inner,
+                       double alpha, int accumulate, void* stream);
+int fdx_axis_apply_f64(fdx_plan_t plan, const double* x, double* out, int64_t outer, int64_t inner,
+                       double alpha, int accumulate, void* stream);
+
+/* ---- fused 3-D operators on a C-contiguous (n0, n1, n2) grid; plans[k] acts along axis k and
+ * plans[k]->n == n_k.  One pass: every input plane is read once, every output written once.
+ *
+ * Slab arguments (multi-GPU halo exchange along axis 0, single GPU passes the defaults):
+ *   z_begin,z_end : only output planes [z_begin, z_end) are computed/written (default 0, n0);
+ *   halo_lo,halo_hi : planes [-halo_lo, n0+halo_hi) of every INPUT are addressable around the
+ *                     logical origin the pointer designates (default 0, 0).  A plan with nl == 0
+ *                     (nr == 0) along axis 0 reads its lower (upper) halo instead of using a
+ *                     boundary band.                                                         */
+typedef struct {
+  int32_t z_begin, z_end;
+  int32_t halo_lo, halo_hi;
+} fdx_slab;
+
+/* laplacian (finite_diff.py:532-575):  out = sum_k alpha[k] * D_k x                         */
+int fdx_laplacian3d_f32(const fdx_plan_t plans[3], const float* x, float* out, const double alpha[3],
+                        const fdx_slab* slab, void* stream);
+int fdx_laplacian3d_f64(const fdx_plan_t plans[3], const double* x, double* out, const double alpha[3],
+                        const fdx_slab* slab, void* stream);
+
+/* divergence (finite_diff.py:404-457): out = sum_k alpha[k] * D_k x_k                       */
+int fdx_divergence3d_f32(const fdx_plan_t plans[3], const float* const x[3], float* out,
+                         const double alpha[3], const fdx_slab* slab, void* stream);
+int fdx_divergence3d_f64(const fdx_plan_t plans[3], const double* const x[3], double* out,
+                         const double alpha[3], const fdx_slab* slab, void* stream);
+
+/* gradient (finite_diff.py:300-351):   out_k = alpha[k] * D_k x
+ * (with transposed plans this is also the adjoint of divergence)                            */
+int fdx_gradient3d_f32(const fdx_plan_t plans[3], const float* x, float* const out[3],
+                       const double alpha[3], const fdx_slab* slab, void* stream);
+int fdx_gradient3d_f64(const fdx_plan_t plans[3], const double* x, double* const out[3],
+                       const double alpha[3], const fdx_slab* slab, void* stream);
+
+/* curl (finite_diff.py:609-668):
+ *   out_0 = alpha[1] D_1 x_2 - alpha[2] D_2 x_1
+ *   out_1 = alpha[2] D_2 x_0 - alpha[0] D_0 x_2
+ *   out_2 = alpha[0] D_0 x_1 - alpha[1] D_1 x_0
+ * (with transposed plans and negated alpha this is also its own adjoint)                    */
+int fdx_curl3d_f32(const fdx_plan_t plans[3], const float* const x[3], float* const out[3],
+                   const double alpha[3], const fdx_slab* slab, void* stream);
+int fdx_curl3d_f64(const fdx_plan_t plans[3], const double* const x[3], double* const out[3],
+                   const double alpha[3], const fdx_slab* slab, void* stream);
+
+/* ---- introspection */
+int fdx_version(void);                 /* 1000*major + minor */
+const char* fdx_error_string(int code); /* static string for FDX_E* and cudaError_t values */
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t fdx_launch_count(void);
+/* name of the kernel family the last call on this thread dispatched to ("axis_stream", ...) */
+const char* fdx_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDX_B200_H_ */
