@@ -16,8 +16,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(LIBDIR, "libfdx_b200.so")
-SOURCES = ("fdx_plan.cu", "fdx_axis.cu", "fdx_fused3d.cu")
+SOURCES = ("fdx_plan.cu", "fdx_axis.cu", "fdx_fused3d_lap.cu", "fdx_fused3d_div.cu", "fdx_fused3d_grad.cu", "fdx_fused3d_curl.cu")
 NVCC_FLAGS = [
+    *(["-DFDX_SWEEP"] if os.environ.get("FDX_SWEEP") else []),
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",

@@ -12,6 +12,8 @@ struct fdx_plan_s {
   double main_taps[FDX_MAX_TAPS];
   double* band_l;  // device, nl*wl
   double* band_r;  // device, nr*wr
+  double* h_band_l;  // host copies (the fused kernels carry the bands in their parameter block)
+  double* h_band_r;
   int device;
 };
 

@@ -1,0 +1,918 @@
+// Fused single-pass 3-D operators: laplacian, divergence, gradient, curl  (include/fdx_b200.h).
+//
+// The reference computes each of these as 3-6 separate `difference` passes plus adds/stack
+// (finitediffx/_src/finite_diff.py:338-351, 443-453, 565-575, 616-668).  Here one kernel reads
+// every input plane once and writes every output once.
+//
+// Design (sm_100a):
+//   * grid of (y,x) tiles x z-chunks; a CTA marches its tile along z (axis 0, the slowest axis);
+//   * a producer warp streams one (TY+2P) x (TX+2HX) halo box per input field and plane into a
+//     multi-stage shared-memory ring with TMA (cp.async.bulk.tensor, mbarrier full/empty pairs);
+//     out-of-range halo elements are zero-filled by the TMA unit, so the main path has no bounds
+//     checks;
+//   * consumer threads own RY rows x 16 bytes (4 fp32 / 2 fp64) of the tile.  In-plane taps come
+//     from shared memory with 128-bit loads; along z each incoming plane is scattered into a
+//     register queue of 2P+1 partial sums per point, so a plane lives in shared memory for one
+//     step only and every output is written exactly once with a 128-bit store;
+//   * rows/columns/planes next to a physical boundary use the plan's dense band taps (the
+//     reference's one-sided stencils or their transposes): those few points re-gather their taps
+//     from global memory (L2-resident, the planes were just streamed).
+//   * multi-GPU slabs: with halo_lo/halo_hi the z march simply starts in the halo planes.
+//
+// Anything this kernel does not cover (non-central plans, mixed radii, unaligned shapes) falls
+// back -- inside the library, still on the GPU -- to the composition of axis kernels.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <mutex>
+#include <type_traits>
+
+#pragma once
+#include "fdx_common.cuh"
+
+extern "C" int fdx_axis_apply_f32(fdx_plan_t, const float*, float*, int64_t, int64_t, double, int, void*);
+extern "C" int fdx_axis_apply_f64(fdx_plan_t, const double*, double*, int64_t, int64_t, double, int, void*);
+
+namespace fdx {
+
+enum Op { LAP = 0, DIV = 1, GRAD = 2, CURL = 3 };
+
+// ------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------ parameters
+constexpr int kTabMax = 640;   // band coefficients of all 6 sides, carried in the parameter block
+constexpr int kRowsMax = 96;   // band rows of all 6 sides
+
+template <typename T>
+struct AxisDev {
+  int n, nl, wl, nr, wr;
+  int tab_l, tab_r;   // offsets of the dense band taps inside FusedParams::tab
+  int rng_l, rng_r;   // offsets of the per-row nonzero ranges inside FusedParams::rng
+  T alpha;            // scale applied on the band path
+  T c[FDX_MAX_TAPS];  // main taps, pre-multiplied by alpha
+};
+
+template <typename T>
+struct FusedParams {
+  CUtensorMap tmap[3];  // one per input field
+  const T* in[3];       // logical plane 0 of each input field (band gathers)
+  T* out[3];
+  AxisDev<T> ax[3];
+  int z_begin, z_end;  // output planes
+  int z_lo, z_hi;      // addressable input planes [z_lo, z_hi]
+  int halo_lo;         // tensor-map plane 0 is logical plane -halo_lo
+  int chunk, n_chunks, tiles_x, tiles_y;
+  short2 rng[kRowsMax];  // [first, last+1) nonzero band column of every band row
+  T tab[kTabMax];
+};
+
+template <int TXV_, int TYT_, int RY_, int STAGES_, int MINB_ = 1>
+struct Cfg {
+  static constexpr int TXV = TXV_, TYT = TYT_, RY = RY_, STAGES = STAGES_, MINB = MINB_;
+};
+
+template <Op OP>
+struct OpTraits;
+template <>
+struct OpTraits<LAP> {
+  static constexpr int NIN = 1, NOUT = 1, NACC = 1;
+  __host__ __device__ static constexpr bool hx(int f) { return f == 0; }
+  __host__ __device__ static constexpr bool hy(int f) { return f == 0; }
+};
+template <>
+struct OpTraits<DIV> {
+  static constexpr int NIN = 3, NOUT = 1, NACC = 1;
+  __host__ __device__ static constexpr bool hx(int f) { return f == 2; }
+  __host__ __device__ static constexpr bool hy(int f) { return f == 1; }
+};
+template <>
+struct OpTraits<GRAD> {
+  static constexpr int NIN = 1, NOUT = 3, NACC = 1;
+  __host__ __device__ static constexpr bool hx(int f) { return f == 0; }
+  __host__ __device__ static constexpr bool hy(int f) { return f == 0; }
+};
+template <>
+struct OpTraits<CURL> {
+  static constexpr int NIN = 3, NOUT = 3, NACC = 2;
+  __host__ __device__ static constexpr bool hx(int f) { return f == 0 || f == 1; }
+  __host__ __device__ static constexpr bool hy(int f) { return f == 0 || f == 2; }
+};
+
+template <Op OP, typename T, int P, typename CFG>
+struct Geometry {
+  using Tr = OpTraits<OP>;
+  static constexpr int V = 16 / sizeof(T);
+  static constexpr int HXV = (P + V - 1) / V;  // halo vectors each side in x
+  static constexpr int HX = HXV * V;
+  static constexpr int TX = CFG::TXV * V, TY = CFG::TYT * CFG::RY;
+  static constexpr int NT = CFG::TXV * CFG::TYT;  // threads; all of them consume, thread 0 also issues TMA
+  static constexpr int WZ = 2 * P + 1;
+  __host__ __device__ static constexpr int xoff(int f) { return Tr::hx(f) ? HX : 0; }
+  __host__ __device__ static constexpr int yoff(int f) { return Tr::hy(f) ? P : 0; }
+  __host__ __device__ static constexpr int box_x(int f) { return TX + 2 * xoff(f); }
+  __host__ __device__ static constexpr int box_y(int f) { return TY + 2 * yoff(f); }
+  __host__ __device__ static constexpr int field_bytes(int f) { return ((box_x(f) * box_y(f) * (int)sizeof(T) + 127) / 128) * 128; }
+  __host__ __device__ static constexpr int field_off(int f) { return f == 0 ? 0 : field_off(f - 1) + field_bytes(f - 1); }
+  static constexpr int STAGE_BYTES = field_off(Tr::NIN);
+  __host__ __device__ static constexpr int tx_bytes() {
+    int b = 0;
+    for (int f = 0; f < Tr::NIN; ++f) b += box_x(f) * box_y(f) * (int)sizeof(T);
+    return b;
+  }
+  static constexpr int SMEM_BYTES = 512 + CFG::STAGES * STAGE_BYTES;  // barriers + alignment slack
+};
+
+template <int N>
+using IC = std::integral_constant<int, N>;
+
+// ------------------------------------------------------------------------------ vector FMA
+// acc += c * x on 16-byte vectors.  fp32 uses the packed FFMA2 (fma.rn.f32x2, sm_100+): the
+// coefficient is a uniform-register scalar broadcast to both halves, so one instruction issues two
+// FMAs -- this kernel is bound by issue slots, not by the FP32 pipe.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long p, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+template <bool INIT>
+__device__ __forceinline__ void fma_vec(Vec<float, 4>& acc, float c, const Vec<float, 4>& x) {
+  const unsigned long long cc = pack2(c, c);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    unsigned long long a = INIT ? 0ull : pack2(acc.v[2 * h], acc.v[2 * h + 1]);
+    const unsigned long long xx = pack2(x.v[2 * h], x.v[2 * h + 1]);
+    if constexpr (INIT)
+      asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(cc), "l"(xx));
+    else
+      asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(cc), "l"(xx));
+    unpack2(a, acc.v[2 * h], acc.v[2 * h + 1]);
+  }
+}
+template <bool INIT>
+__device__ __forceinline__ void fma_vec(Vec<double, 2>& acc, double c, const Vec<double, 2>& x) {
+#pragma unroll
+  for (int v = 0; v < 2; ++v) acc.v[v] = INIT ? c * x.v[v] : fma(c, x.v[v], acc.v[v]);
+}
+__device__ __forceinline__ void add_vec(Vec<float, 4>& acc, const Vec<float, 4>& x) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    unsigned long long a = pack2(acc.v[2 * h], acc.v[2 * h + 1]);
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(pack2(x.v[2 * h], x.v[2 * h + 1])));
+    unpack2(a, acc.v[2 * h], acc.v[2 * h + 1]);
+  }
+}
+__device__ __forceinline__ void add_vec(Vec<double, 2>& acc, const Vec<double, 2>& x) {
+#pragma unroll
+  for (int v = 0; v < 2; ++v) acc.v[v] += x.v[v];
+}
+
+// ------------------------------------------------------------------------------ the kernel
+template <Op OP, typename T, int P, typename CFG>
+__global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
+    fused3d_kernel(const __grid_constant__ FusedParams<T> prm) {
+  using G = Geometry<OP, T, P, CFG>;
+  using Tr = OpTraits<OP>;
+  constexpr int V = G::V, RY = CFG::RY, WZ = G::WZ, STAGES = CFG::STAGES, HX = G::HX, HXV = G::HXV;
+  constexpr int TRW = 32 / CFG::TXV;  // thread rows per warp
+  constexpr int WR = TRW * RY;        // grid rows per warp
+  static_assert(CFG::TXV == 16 || CFG::TXV == 32, "a warp must cover whole tile rows");
+  using VT = Vec<T, V>;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // barriers first, then the stage ring rounded up to 128 B for TMA; offsets (not re-derived
+  // pointers) so the compiler keeps the shared address space and emits LDS
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty_bar = full_bar + STAGES;
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t ring_off = ((raw_u32 + 256u + 127u) & ~127u) - raw_u32;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int n0 = prm.ax[0].n, n1 = prm.ax[1].n, n2 = prm.ax[2].n;
+
+  // ---- work item: (tile, chunk); tile fastest so that concurrently resident CTAs share halos in L2
+  int b = blockIdx.x;
+  const int tile_x = b % prm.tiles_x;
+  b /= prm.tiles_x;
+  const int tile_y = b % prm.tiles_y;
+  const int chunk = b / prm.tiles_y;
+  const int x0 = tile_x * G::TX, y0 = tile_y * G::TY;
+  const int zs = prm.z_begin + chunk * prm.chunk;
+  const int ze = min(prm.z_end, zs + prm.chunk);
+  const int zin0 = max(zs - P, prm.z_lo);
+  const int zin1 = min(ze - 1 + P, prm.z_hi);
+  const int n_planes = zin1 - zin0 + 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], G::NT / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // TMA issue (thread 0 only): plane `it` of this CTA's march goes to stage it % STAGES
+  auto issue = [&](int it) {
+    const int s = it % STAGES;
+    if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);  // all warps released it
+    mbar_expect_tx(&full_bar[s], G::tx_bytes());
+    unsigned char* dst = smem_raw + ring_off + (size_t)s * G::STAGE_BYTES;
+    const int zc = zin0 + it + prm.halo_lo;
+#pragma unroll
+    for (int f = 0; f < Tr::NIN; ++f)
+      tma_load_3d(dst + G::field_off(f), &prm.tmap[f], &full_bar[s], x0 - G::xoff(f), y0 - G::yoff(f), zc);
+  };
+  if (tid == 0) {
+    for (int f = 0; f < Tr::NIN; ++f) asm volatile("prefetch.tensormap [%0];" ::"l"(&prm.tmap[f]) : "memory");
+    for (int it = 0; it < STAGES - 1 && it < n_planes; ++it) issue(it);
+  }
+
+  const int tx = tid % CFG::TXV, ty = tid / CFG::TXV;
+  const int xg = x0 + tx * V;   // first global x of this thread's vector
+  const int yg = y0 + ty * RY;  // first global y of this thread's rows
+  const AxisDev<T>& A0 = prm.ax[0];
+  const AxisDev<T>& A1 = prm.ax[1];
+  const AxisDev<T>& A2 = prm.ax[2];
+  const int64_t plane = (int64_t)n1 * n2;
+  // n2 % V == 0, so a vector is entirely in or out of the grid
+  bool rok[RY];
+#pragma unroll
+  for (int j = 0; j < RY; ++j) rok[j] = (xg < n2) && (yg + j < n1);
+  const bool yband = rok[0] && ((yg < A1.nl) || (yg + RY > n1 - A1.nr));
+  // CTA-uniform: does this tile touch the physical x boundary on the left / right?
+  const bool xedge_l = x0 < A2.nl;
+  const bool xedge_r = x0 + G::TX > n2 - A2.nr;
+  const int64_t thread_ofs = (int64_t)yg * n2 + xg;  // this thread's first element inside a plane
+  // element offset of this thread's vector in tile row ty*RY of each field (constant per thread)
+  int toff[Tr::NIN];
+#pragma unroll
+  for (int f = 0; f < Tr::NIN; ++f) toff[f] = (ty * RY) * G::box_x(f) + G::xoff(f) + tx * V;
+
+  VT acc[Tr::NACC][WZ][RY];
+#pragma unroll
+  for (int a = 0; a < Tr::NACC; ++a)
+#pragma unroll
+    for (int s = 0; s < WZ; ++s)
+#pragma unroll
+      for (int j = 0; j < RY; ++j)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[a][s][j].v[v] = 0;
+
+  // ------------------------------------------------------------------ hot in-plane helpers
+  // D_y for output row j from centre rows c[j .. j+2P]
+  auto dy_main = [&](const VT* c, int j) {
+    VT r;
+    fma_vec<true>(r, A1.c[0], c[j]);
+#pragma unroll
+    for (int k = 1; k < WZ; ++k) fma_vec<false>(r, A1.c[k], c[j + k]);
+    return r;
+  };
+  // D_x for one row: `rowp` points at this thread's vector inside a tile row that has x halos
+  auto dx_main = [&](const T* rowp, const VT& centre) {
+    T w[(2 * HXV + 1) * V];
+#pragma unroll
+    for (int u = 0; u < HXV; ++u) {
+      const VT l = *reinterpret_cast<const VT*>(rowp - (HXV - u) * V);
+      const VT rr = *reinterpret_cast<const VT*>(rowp + (u + 1) * V);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        w[u * V + v] = l.v[v];
+        w[(HXV + 1 + u) * V + v] = rr.v[v];
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) w[HXV * V + v] = centre.v[v];
+    VT r;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      T s = A2.c[0] * w[HX + v - P];
+#pragma unroll
+      for (int k = 1; k < WZ; ++k) s = fma(A2.c[k], w[HX + v - P + k], s);
+      r.v[v] = s;
+    }
+    return r;
+  };
+
+  // ------------------------------------------------------------------ cold band helpers
+  // band row/column/plane i of axis A: coefficient offset, nonzero column range, first band column
+  auto band_rng = [&](const AxisDev<T>& A, int i, int& tab, int& c0, int& c1, int& colbase) {
+    const bool left = i < A.nl;
+    const int r = left ? i : i - (A.n - A.nr);
+    const int w = left ? A.wl : A.wr;
+    tab = (left ? A.tab_l : A.tab_r) + r * w;
+    const short2 rg = prm.rng[(left ? A.rng_l : A.rng_r) + r];
+    c0 = rg.x, c1 = rg.y;
+    colbase = left ? 0 : A.n - A.wr;
+  };
+  // y band of global row y: taps from the tile when it holds all of them, else from global memory.
+  // tcol: smem address of (tile row 0, this thread's x); gcol: global address of (z, row 0, xg)
+  auto band_y = [&](const T* tcol, int pitch, int boxy, const T* gcol, int y) {
+    int tab, c0, c1, cb;
+    band_rng(A1, y, tab, c0, c1, cb);
+    VT a;
+#pragma unroll
+    for (int v = 0; v < V; ++v) a.v[v] = 0;
+    const int r0 = cb + c0 - (y0 - P);
+    if (r0 >= 0 && r0 + (c1 - c0) <= boxy) {
+      const T* p = tcol + r0 * pitch;
+      for (int c = c0; c < c1; ++c, p += pitch) {
+        const T cf = prm.tab[tab + c];
+        const VT x = *reinterpret_cast<const VT*>(p);
+#pragma unroll
+        for (int v = 0; v < V; ++v) a.v[v] = fma(cf, x.v[v], a.v[v]);
+      }
+    } else {
+      const T* p = gcol + (int64_t)(cb + c0) * n2;
+      for (int c = c0; c < c1; ++c, p += n2) {
+        const T cf = prm.tab[tab + c];
+        const VT x = ld_cached<T, V>(p);
+#pragma unroll
+        for (int v = 0; v < V; ++v) a.v[v] = fma(cf, x.v[v], a.v[v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) a.v[v] *= A1.alpha;
+    return a;
+  };
+  // x bands, warp-cooperative: lanes are re-mapped to (grid row of this warp, band vector) so that
+  // the few boundary columns of all WR rows of the warp are evaluated side by side from the tile in
+  // shared memory; results travel back to the owning lanes with shuffles.  `tilef` = tile of a field
+  // with x halos, `yo` its y halo offset, xs[] the per-row D_x vectors to patch.
+  auto xband_pass = [&](const T* tilef, int pitch, int yo, bool right, VT (&xs)[RY]) {
+    const int wrow0 = (tid / 32) * WR;  // first tile row of this warp
+    const int r = lane % WR, g = lane / WR;
+    // first owner vector (tile-relative) that intersects the band
+    const int v0 = right ? max(0, (n2 - A2.nr - x0) / V) : 0;
+    const int vx = v0 + g;  // owner vector handled by this lane
+    VT bv;
+#pragma unroll
+    for (int v = 0; v < V; ++v) bv.v[v] = 0;
+    const int yrow = y0 + wrow0 + r;
+    if (vx < CFG::TXV && yrow < n1) {
+      const T* row = tilef + (wrow0 + r + yo) * pitch;  // tile column 0 <-> global x0 - HX
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int x = x0 + vx * V + v;
+        if (x < n2 && (right ? x >= n2 - A2.nr : x < A2.nl)) {
+          int tab, c0, c1, cb;
+          band_rng(A2, x, tab, c0, c1, cb);
+          const int s0 = cb - (x0 - HX);
+          T a = 0;
+          for (int c = c0; c < c1; ++c) a = fma(prm.tab[tab + c], row[s0 + c], a);
+          bv.v[v] = a * A2.alpha;
+        }
+      }
+    }
+    // deliver to the owners: the thread (tx, ty) owns vector tx of rows ty*RY + j
+    const int gsrc = tx - v0;
+    const int trow = (ty % TRW) * RY;
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      const int src = (gsrc >= 0 ? gsrc : 0) * WR + trow + j;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const T got = __shfl_sync(0xffffffffu, bv.v[v], src & 31);
+        const int x = xg + v;
+        if (gsrc >= 0 && (right ? (x >= n2 - A2.nr) : (x < A2.nl))) xs[j].v[v] = got;
+      }
+    }
+  };
+  auto xband_fix = [&](const T* tilef, int pitch, int yo, VT (&xs)[RY]) {
+    if (xedge_l) xband_pass(tilef, pitch, yo, false, xs);
+    if (xedge_r) xband_pass(tilef, pitch, yo, true, xs);
+  };
+  // z band of plane z (always from global memory: the other planes are not in the ring)
+  auto band_z = [&](const T* gcol0 /* global address of (plane 0, this row, xg) */, int z) {
+    int tab, c0, c1, cb;
+    band_rng(A0, z, tab, c0, c1, cb);
+    VT a;
+#pragma unroll
+    for (int v = 0; v < V; ++v) a.v[v] = 0;
+    const T* p = gcol0 + (int64_t)(cb + c0) * plane;
+#pragma unroll 2
+    for (int c = c0; c < c1; ++c, p += plane) {
+      const T cf = prm.tab[tab + c];
+      const VT x = ld_cached<T, V>(p);
+#pragma unroll
+      for (int v = 0; v < V; ++v) a.v[v] = fma(cf, x.v[v], a.v[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) a.v[v] *= A0.alpha;
+    return a;
+  };
+  auto zband = [&](int z) { return z < A0.nl || z >= n0 - A0.nr; };
+  auto is_yband = [&](int j) { return rok[j] && (yg + j < A1.nl || yg + j >= n1 - A1.nr); };
+  auto store = [&](int o, int z, int j, const VT& val) {
+    if (rok[j]) st_vec<T, V>(prm.out[o] + (int64_t)z * plane + thread_ofs + (int64_t)j * n2, val);
+  };
+
+  // ---- march along z ---------------------------------------------------------------------
+  int u = 0;  // it % WZ
+  for (int it = 0; it < n_planes; ++it) {
+    const int zc = zin0 + it;
+    const int s = it % STAGES;
+    const bool inr = (zc >= zs) && (zc < ze);  // this plane is also an output plane of ours
+    const bool zb = inr && zband(zc);
+    // keep STAGES-1 planes in flight: the stage consumed at step it-1 is refilled now
+    if (tid == 0 && it + STAGES - 1 < n_planes) issue(it + STAGES - 1);
+    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+    const unsigned char* st = smem_raw + ring_off + (size_t)s * G::STAGE_BYTES;
+    auto tile = [&](int f) { return reinterpret_cast<const T*>(st + G::field_off(f)); };
+    // address of this thread's vector in tile row (ty*RY + i) of field f
+    auto tptr = [&](int f, int i) { return tile(f) + toff[f] + i * G::box_x(f); };
+    const int64_t zofs = (int64_t)zc * plane;
+
+    VT zv[Tr::NACC][RY];   // values scattered along z
+    VT tin[Tr::NACC][RY];  // in-plane contribution to plane zc of each accumulator set
+    // ---------------- in-plane part (one copy of this code: it does not depend on the queue phase)
+    if constexpr (OP == LAP || OP == GRAD) {
+      VT c[RY + 2 * P];
+#pragma unroll
+      for (int i = 0; i < RY + 2 * P; ++i) c[i] = *reinterpret_cast<const VT*>(tptr(0, i));
+#pragma unroll
+      for (int j = 0; j < RY; ++j) zv[0][j] = c[j + P];
+      if (inr) {
+        VT ys[RY], xs[RY];
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          ys[j] = dy_main(c, j);
+          xs[j] = dx_main(tptr(0, j + P), c[j + P]);
+        }
+        if (yband) {
+#pragma unroll
+          for (int j = 0; j < RY; ++j)
+            if (is_yband(j)) ys[j] = band_y(tile(0) + HX + tx * V, G::box_x(0), G::box_y(0), prm.in[0] + zofs + xg, yg + j);
+        }
+        if (xedge_l || xedge_r) xband_fix(tile(0), G::box_x(0), P, xs);
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          if constexpr (OP == LAP) {
+            tin[0][j] = ys[j];
+            add_vec(tin[0][j], xs[j]);
+          } else {
+            store(1, zc, j, ys[j]);
+            store(2, zc, j, xs[j]);
+          }
+        }
+      }
+    } else if constexpr (OP == DIV) {
+#pragma unroll
+      for (int j = 0; j < RY; ++j) zv[0][j] = *reinterpret_cast<const VT*>(tptr(0, j));
+      if (inr) {
+        VT c[RY + 2 * P];
+#pragma unroll
+        for (int i = 0; i < RY + 2 * P; ++i) c[i] = *reinterpret_cast<const VT*>(tptr(1, i));
+        VT ys[RY], xs[RY];
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          ys[j] = dy_main(c, j);
+          const VT ctr = *reinterpret_cast<const VT*>(tptr(2, j));
+          xs[j] = dx_main(tptr(2, j), ctr);
+        }
+        if (yband) {
+#pragma unroll
+          for (int j = 0; j < RY; ++j)
+            if (is_yband(j)) ys[j] = band_y(tile(1) + tx * V, G::box_x(1), G::box_y(1), prm.in[1] + zofs + xg, yg + j);
+        }
+        if (xedge_l || xedge_r) xband_fix(tile(2), G::box_x(2), 0, xs);
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          tin[0][j] = ys[j];
+          add_vec(tin[0][j], xs[j]);
+        }
+      }
+    } else {  // CURL
+      // out_0 = D1 x2 - D2 x1 ; out_1 = D2 x0 - D0 x2 (acc set 0) ; out_2 = D0 x1 - D1 x0 (acc set 1)
+      VT c2[RY + 2 * P];
+#pragma unroll
+      for (int i = 0; i < RY + 2 * P; ++i) c2[i] = *reinterpret_cast<const VT*>(tptr(2, i));
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        zv[0][j] = c2[j + P];                                  // x2 -> -D0 x2 into out_1
+        zv[1][j] = *reinterpret_cast<const VT*>(tptr(1, j));    // x1 -> +D0 x1 into out_2
+      }
+      if (inr) {
+        VT c0[RY + 2 * P];
+#pragma unroll
+        for (int i = 0; i < RY + 2 * P; ++i) c0[i] = *reinterpret_cast<const VT*>(tptr(0, i));
+        VT y2[RY], x1[RY], y0v[RY], x0v[RY];
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          y2[j] = dy_main(c2, j);                          // D1 x2
+          x1[j] = dx_main(tptr(1, j), zv[1][j]);           // D2 x1
+          y0v[j] = dy_main(c0, j);                         // D1 x0
+          x0v[j] = dx_main(tptr(0, j + P), c0[j + P]);     // D2 x0
+        }
+        if (yband) {
+#pragma unroll
+          for (int j = 0; j < RY; ++j)
+            if (is_yband(j)) {
+              y2[j] = band_y(tile(2) + tx * V, G::box_x(2), G::box_y(2), prm.in[2] + zofs + xg, yg + j);
+              y0v[j] = band_y(tile(0) + HX + tx * V, G::box_x(0), G::box_y(0), prm.in[0] + zofs + xg, yg + j);
+            }
+        }
+        if (xedge_l || xedge_r) {
+          xband_fix(tile(1), G::box_x(1), 0, x1);
+          xband_fix(tile(0), G::box_x(0), P, x0v);
+        }
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          VT o0;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            o0.v[v] = y2[j].v[v] - x1[j].v[v];
+            tin[0][j].v[v] = x0v[j].v[v];
+            tin[1][j].v[v] = -y0v[j].v[v];
+          }
+          store(0, zc, j, o0);
+        }
+      }
+    }
+    // this warp no longer reads the stage: release it (one arrive per warp)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+    // ---------------- planes next to a physical z boundary: one-sided taps, gathered directly
+    if (zb) {
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        if (!rok[j]) continue;
+        const int64_t cofs = thread_ofs + (int64_t)j * n2;
+        if constexpr (OP == LAP || OP == DIV || OP == GRAD) {
+          VT zz = band_z(prm.in[0] + cofs, zc);
+          if constexpr (OP != GRAD) add_vec(zz, tin[0][j]);
+          store(0, zc, j, zz);
+        } else {
+          const VT z2 = band_z(prm.in[2] + cofs, zc), z1 = band_z(prm.in[1] + cofs, zc);
+          VT o1, o2;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            o1.v[v] = tin[0][j].v[v] - z2.v[v];
+            o2.v[v] = tin[1][j].v[v] + z1.v[v];
+          }
+          store(1, zc, j, o1);
+          store(2, zc, j, o2);
+        }
+      }
+    }
+    const bool add_tin = inr && !zb && (OP != GRAD);
+    const int zo = zc - P;
+    const bool emit = (zo >= zs) && (zo < ze) && !zband(zo);
+
+    // ---------------- scatter along z into the register queue (WZ copies, one per queue phase):
+    // plane zc feeds output z' = zc + P - k with tap k; slot(z') = (it - k) mod WZ
+    auto phase = [&](auto U_) {
+      constexpr int U = decltype(U_)::value;
+#pragma unroll
+      for (int a = 0; a < Tr::NACC; ++a) {
+#pragma unroll
+        for (int k = 0; k < WZ; ++k) {
+          const int slot = ((U - k) % WZ + WZ) % WZ;
+          const T cz = (OP == CURL && a == 0) ? -A0.c[k] : A0.c[k];
+#pragma unroll
+          for (int j = 0; j < RY; ++j) {
+            if (k == 0)
+              fma_vec<true>(acc[a][slot][j], cz, zv[a][j]);
+            else
+              fma_vec<false>(acc[a][slot][j], cz, zv[a][j]);
+          }
+        }
+      }
+      if (add_tin) {  // in-plane part of plane zc goes to the slot of z' = zc (tap k = P)
+        const int slot_c = ((U - P) % WZ + WZ) % WZ;
+#pragma unroll
+        for (int a = 0; a < Tr::NACC; ++a)
+#pragma unroll
+          for (int j = 0; j < RY; ++j) add_vec(acc[a][slot_c][j], tin[a][j]);
+      }
+      if (emit) {  // the output plane zc - P is complete
+        const int slot_o = ((U - 2 * P) % WZ + WZ) % WZ;
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          if constexpr (OP == LAP || OP == DIV || OP == GRAD) {
+            store(0, zo, j, acc[0][slot_o][j]);
+          } else {
+            store(1, zo, j, acc[0][slot_o][j]);
+            store(2, zo, j, acc[1][slot_o][j]);
+          }
+        }
+      }
+    };
+    switch (u) {
+      case 0: phase(IC<0>{}); break;
+      case 1: phase(IC<1>{}); break;
+      case 2: phase(IC<2>{}); break;
+      case 3: if constexpr (WZ > 3) phase(IC<3>{}); break;
+      case 4: if constexpr (WZ > 4) phase(IC<4>{}); break;
+      case 5: if constexpr (WZ > 5) phase(IC<5>{}); break;
+      case 6: if constexpr (WZ > 6) phase(IC<6>{}); break;
+      case 7: if constexpr (WZ > 7) phase(IC<7>{}); break;
+      case 8: if constexpr (WZ > 8) phase(IC<8>{}); break;
+      default: break;
+    }
+    u = (u + 1 == WZ) ? 0 : u + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+template <typename T>
+static int make_tmap(CUtensorMap* m, const T* base, int64_t n2, int64_t n1, int64_t nz, int bx, int by) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return FDX_EUNSUPPORTED;
+  cuuint64_t dims[3] = {(cuuint64_t)n2, (cuuint64_t)n1, (cuuint64_t)nz};
+  cuuint64_t strides[2] = {(cuuint64_t)n2 * sizeof(T), (cuuint64_t)n2 * n1 * sizeof(T)};
+  cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FDX_OK : FDX_EUNSUPPORTED;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return s ? std::atoi(s) : dflt;
+}
+
+struct SlabArgs {
+  int z_begin, z_end, halo_lo, halo_hi;
+};
+
+static SlabArgs slab_args(const fdx_plan_t plans[3], const fdx_slab* s) {
+  if (!s) return SlabArgs{0, plans[0]->n, 0, 0};
+  return SlabArgs{s->z_begin, s->z_end, s->halo_lo, s->halo_hi};
+}
+
+template <Op OP, typename T, int P, typename CFG>
+static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const out[3], const double alpha[3],
+                      const SlabArgs& sl, cudaStream_t st) {
+  using G = Geometry<OP, T, P, CFG>;
+  using Tr = OpTraits<OP>;
+  const int n0 = plans[0]->n, n1 = plans[1]->n, n2 = plans[2]->n;
+  FusedParams<T> prm;
+  for (int f = 0; f < 3; ++f) {
+    prm.in[f] = f < Tr::NIN ? in[f] : nullptr;
+    prm.out[f] = f < Tr::NOUT ? out[f] : nullptr;
+  }
+  int tab_used = 0, rows_used = 0;
+  for (int k = 0; k < 3; ++k) {
+    const fdx_plan_s* p = plans[k];
+    AxisDev<T>& a = prm.ax[k];
+    a.n = p->n, a.nl = p->nl, a.wl = p->wl, a.nr = p->nr, a.wr = p->wr;
+    a.alpha = (T)alpha[k];
+    for (int t = 0; t < FDX_MAX_TAPS; ++t) a.c[t] = t < 2 * P + 1 ? (T)(p->main_taps[t] * alpha[k]) : (T)0;
+    for (int side = 0; side < 2; ++side) {
+      const int rows = side ? p->nr : p->nl, w = side ? p->wr : p->wl;
+      const double* h = side ? p->h_band_r : p->h_band_l;
+      if (tab_used + rows * w > kTabMax || rows_used + rows > kRowsMax) return FDX_EUNSUPPORTED;
+      (side ? a.tab_r : a.tab_l) = tab_used;
+      (side ? a.rng_r : a.rng_l) = rows_used;
+      for (int r = 0; r < rows; ++r) {
+        int c0 = w, c1 = 0;
+        for (int c = 0; c < w; ++c) {
+          prm.tab[tab_used + r * w + c] = (T)h[r * w + c];
+          if (h[r * w + c] != 0.0) {
+            if (c < c0) c0 = c;
+            c1 = c + 1;
+          }
+        }
+        if (c1 <= c0) c0 = c1 = 0;
+        prm.rng[rows_used + r] = make_short2((short)c0, (short)c1);
+      }
+      tab_used += rows * w;
+      rows_used += rows;
+    }
+  }
+  prm.z_begin = sl.z_begin, prm.z_end = sl.z_end;
+  prm.halo_lo = sl.halo_lo;
+  prm.z_lo = -sl.halo_lo, prm.z_hi = n0 - 1 + sl.halo_hi;
+  for (int f = 0; f < Tr::NIN; ++f) {
+    int rc = make_tmap<T>(&prm.tmap[f], in[f] - (int64_t)sl.halo_lo * n1 * n2, n2, n1, (int64_t)n0 + sl.halo_lo + sl.halo_hi,
+                          G::box_x(f), G::box_y(f));
+    if (rc) return rc;
+  }
+  prm.tiles_x = (n2 + G::TX - 1) / G::TX;
+  prm.tiles_y = (n1 + G::TY - 1) / G::TY;
+  const int nz = sl.z_end - sl.z_begin;
+  const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
+  // z chunking: enough CTAs for a few waves, but chunks long enough to amortise the 2P warm-up planes
+  int chunk = env_int("FDX_FUSED_CHUNK", 0);
+  if (chunk <= 0) {
+    const int64_t want = (int64_t)kNumSMs * 6;
+    int64_t nch = (want + tiles - 1) / tiles;
+    chunk = (int)((nz + nch - 1) / nch);
+    const int min_chunk = 16 * P;
+    if (chunk < min_chunk) chunk = min_chunk;
+  }
+  if (chunk > nz) chunk = nz;
+  prm.chunk = chunk;
+  prm.n_chunks = (nz + chunk - 1) / chunk;
+  const int64_t blocks = tiles * prm.n_chunks;
+  if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
+  auto kern = fused3d_kernel<OP, T, P, CFG>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<(unsigned)blocks, G::NT, G::SMEM_BYTES, st>>>(prm);
+  count_launch(OP == LAP ? "fused_laplacian3d" : OP == DIV ? "fused_divergence3d" : OP == GRAD ? "fused_gradient3d" : "fused_curl3d");
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+template <Op OP, typename T, int P>
+static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const out[3], const double alpha[3],
+                    const SlabArgs& sl, cudaStream_t st) {
+  // tile configurations: Cfg<lanes in x, thread rows, rows per thread, stages, min CTAs per SM>
+  const int cfg = env_int("FDX_FUSED_CFG", 0);
+#define FDX_CFG(ID, ...) \
+  case ID:               \
+    return launch_cfg<OP, T, P, Cfg<__VA_ARGS__>>(plans, in, out, alpha, sl, st);
+#ifdef FDX_SWEEP
+  if constexpr (OP == LAP && sizeof(T) == 4 && P == 3) {
+    switch (cfg) {
+      FDX_CFG(1, 16, 16, 2, 4, 1)
+      FDX_CFG(2, 16, 16, 2, 4, 2)
+      FDX_CFG(3, 16, 16, 4, 3, 1)
+      FDX_CFG(4, 16, 32, 2, 4, 1)
+      FDX_CFG(5, 32, 8, 2, 4, 2)
+      FDX_CFG(6, 32, 8, 4, 3, 1)
+      FDX_CFG(7, 32, 16, 2, 3, 1)
+      FDX_CFG(8, 16, 16, 2, 6, 1)
+      FDX_CFG(9, 16, 8, 2, 4, 4)
+      FDX_CFG(10, 16, 8, 4, 4, 2)
+      FDX_CFG(11, 16, 16, 2, 3, 3)
+      default:
+        break;
+    }
+  }
+#endif
+  constexpr bool heavy = (OP == CURL) || (sizeof(T) == 8 && P >= 3);
+  if constexpr (heavy) {
+    switch (cfg) {
+      FDX_CFG(1, 16, 16, 1, 4, 2)
+      default:
+        return launch_cfg<OP, T, P, Cfg<16, 16, 1, 4, 1>>(plans, in, out, alpha, sl, st);
+    }
+  } else {
+    switch (cfg) {
+      FDX_CFG(1, 16, 16, 2, 4, 1)
+      default:
+        return launch_cfg<OP, T, P, Cfg<16, 16, 2, 4, 2>>(plans, in, out, alpha, sl, st);
+    }
+  }
+#undef FDX_CFG
+}
+
+// Can the TMA kernel take this call?  (otherwise: composition of axis kernels)
+template <Op OP, typename T>
+static int fused_radius(const fdx_plan_t plans[3], const T* const in[3], T* const out[3], const SlabArgs& sl) {
+  using Tr = OpTraits<OP>;
+  constexpr int V = 16 / sizeof(T);
+  if (env_int("FDX_FUSED_DISABLE", 0)) return 0;
+  const int P = plans[0]->hi;
+  if (P < 1 || P > 4) return 0;
+  for (int k = 0; k < 3; ++k) {
+    const fdx_plan_s* p = plans[k];
+    if (p->lo != -P || p->hi != P) return 0;
+    if (k > 0 && (p->nl < P || p->nr < P)) return 0;   // in-plane axes never have halos
+    if (p->nl + p->nr > p->n) return 0;                 // dense (tiny-n) plans
+    if (p->n < 1) return 0;
+  }
+  if (plans[0]->nl == 0 ? sl.halo_lo < P : plans[0]->nl < P) return 0;
+  if (plans[0]->nr == 0 ? sl.halo_hi < P : plans[0]->nr < P) return 0;
+  if (plans[2]->n % V != 0) return 0;
+  for (int f = 0; f < Tr::NIN; ++f)
+    if (((uintptr_t)in[f] & 15) != 0) return 0;
+  for (int f = 0; f < Tr::NOUT; ++f)
+    if (((uintptr_t)out[f] & 15) != 0) return 0;
+  if (sl.z_begin < 0 || sl.z_end > plans[0]->n || sl.z_begin >= sl.z_end) return 0;
+  if (!encode_fn()) return 0;
+  return P;
+}
+
+template <typename T>
+static int axis_apply(fdx_plan_t p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, int acc, void* st) {
+  if constexpr (sizeof(T) == 4)
+    return fdx_axis_apply_f32(p, x, out, outer, inner, alpha, acc, st);
+  else
+    return fdx_axis_apply_f64(p, x, out, outer, inner, alpha, acc, st);
+}
+
+// D_k on the (n0, n1, n2) grid through the generic axis kernels
+template <typename T>
+static int apply_axis3(const fdx_plan_t plans[3], int k, const T* x, T* out, double alpha, int acc, void* st) {
+  const int64_t n[3] = {plans[0]->n, plans[1]->n, plans[2]->n};
+  const int64_t outer = (k == 0) ? 1 : (k == 1 ? n[0] : n[0] * n[1]);
+  const int64_t inner = (k == 0) ? n[1] * n[2] : (k == 1 ? n[2] : 1);
+  return axis_apply<T>(plans[k], x, out, outer, inner, alpha, acc, st);
+}
+
+template <Op OP, typename T>
+static int composed(const fdx_plan_t plans[3], const T* const in[3], T* const out[3], const double alpha[3], void* st) {
+  int rc = FDX_OK;
+  if constexpr (OP == LAP) {
+    for (int k = 0; k < 3 && !rc; ++k) rc = apply_axis3<T>(plans, k, in[0], out[0], alpha[k], k > 0, st);
+  } else if constexpr (OP == DIV) {
+    for (int k = 0; k < 3 && !rc; ++k) rc = apply_axis3<T>(plans, k, in[k], out[0], alpha[k], k > 0, st);
+  } else if constexpr (OP == GRAD) {
+    for (int k = 0; k < 3 && !rc; ++k) rc = apply_axis3<T>(plans, k, in[0], out[k], alpha[k], 0, st);
+  } else {
+    const int plus_axis[3] = {1, 2, 0}, plus_comp[3] = {2, 0, 1};
+    const int minus_axis[3] = {2, 0, 1}, minus_comp[3] = {1, 2, 0};
+    for (int c = 0; c < 3 && !rc; ++c) {
+      rc = apply_axis3<T>(plans, plus_axis[c], in[plus_comp[c]], out[c], alpha[plus_axis[c]], 0, st);
+      if (!rc) rc = apply_axis3<T>(plans, minus_axis[c], in[minus_comp[c]], out[c], -alpha[minus_axis[c]], 1, st);
+    }
+  }
+  return rc;
+}
+
+template <Op OP, typename T>
+static int run(const fdx_plan_t plans[3], const T* const in[3], T* const out[3], const double alpha[3],
+               const fdx_slab* slab, void* stream) {
+  using Tr = OpTraits<OP>;
+  if (!plans || !plans[0] || !plans[1] || !plans[2] || !alpha || !in || !out) return FDX_EINVAL;
+  for (int f = 0; f < Tr::NIN; ++f)
+    if (!in[f]) return FDX_EINVAL;
+  for (int f = 0; f < Tr::NOUT; ++f)
+    if (!out[f]) return FDX_EINVAL;
+  const SlabArgs sl = slab_args(plans, slab);
+  if (plans[0]->n == 0 || plans[1]->n == 0 || plans[2]->n == 0) return FDX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = fused_radius<OP, T>(plans, in, out, sl);
+  int rc = FDX_EUNSUPPORTED;
+  switch (P) {
+    case 1:
+      rc = launch_p<OP, T, 1>(plans, in, out, alpha, sl, st);
+      break;
+    case 2:
+      rc = launch_p<OP, T, 2>(plans, in, out, alpha, sl, st);
+      break;
+    case 3:
+      rc = launch_p<OP, T, 3>(plans, in, out, alpha, sl, st);
+      break;
+    case 4:
+      rc = launch_p<OP, T, 4>(plans, in, out, alpha, sl, st);
+      break;
+    default:
+      break;
+  }
+  if (rc != FDX_EUNSUPPORTED) return rc;
+  // fallback: only the whole-grid, no-halo form can be composed from the axis kernels
+  if (sl.z_begin != 0 || sl.z_end != plans[0]->n || sl.halo_lo != 0 || sl.halo_hi != 0) return FDX_EUNSUPPORTED;
+  if (plans[0]->nl + plans[0]->nr == 0 && plans[0]->lo != plans[0]->hi) return FDX_EUNSUPPORTED;
+  return composed<OP, T>(plans, in, out, alpha, stream);
+}
+
+}  // namespace fdx
+

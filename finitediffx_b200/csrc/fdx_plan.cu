@@ -37,15 +37,29 @@ extern "C" int fdx_plan_create(fdx_plan_t* plan, const fdx_axis_desc* d) {
   p->nl = d->nl, p->wl = d->wl, p->nr = d->nr, p->wr = d->wr;
   std::memcpy(p->main_taps, d->main_taps, sizeof(p->main_taps));
   p->band_l = p->band_r = nullptr;
+  p->h_band_l = p->h_band_r = nullptr;
   cudaError_t e = cudaGetDevice(&p->device);
   const size_t bl = sizeof(double) * (size_t)d->nl * d->wl, br = sizeof(double) * (size_t)d->nr * d->wr;
   if (e == cudaSuccess && bl) e = cudaMalloc((void**)&p->band_l, bl);
   if (e == cudaSuccess && bl) e = cudaMemcpy(p->band_l, d->band_l, bl, cudaMemcpyHostToDevice);
   if (e == cudaSuccess && br) e = cudaMalloc((void**)&p->band_r, br);
   if (e == cudaSuccess && br) e = cudaMemcpy(p->band_r, d->band_r, br, cudaMemcpyHostToDevice);
+  auto host_copy = [&](double** dst, const double* src, size_t count) {
+    if (e != cudaSuccess || !count) return;
+    *dst = new (std::nothrow) double[count];
+    if (!*dst) {
+      e = cudaErrorMemoryAllocation;
+      return;
+    }
+    std::memcpy(*dst, src, sizeof(double) * count);
+  };
+  host_copy(&p->h_band_l, d->band_l, (size_t)d->nl * d->wl);
+  host_copy(&p->h_band_r, d->band_r, (size_t)d->nr * d->wr);
   if (e != cudaSuccess) {
     cudaFree(p->band_l);
     cudaFree(p->band_r);
+    delete[] p->h_band_l;
+    delete[] p->h_band_r;
     delete p;
     return (int)e;
   }
@@ -57,6 +71,8 @@ extern "C" int fdx_plan_destroy(fdx_plan_t plan) {
   if (!plan) return FDX_OK;
   cudaFree(plan->band_l);
   cudaFree(plan->band_r);
+  delete[] plan->h_band_l;
+  delete[] plan->h_band_r;
   delete plan;
   return FDX_OK;
 }
