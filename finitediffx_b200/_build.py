@@ -19,6 +19,7 @@ LIB = os.path.join(LIBDIR, "libfdx_b200.so")
 SOURCES = ("fdx_plan.cu", "fdx_axis.cu", "fdx_fused3d_lap.cu", "fdx_fused3d_div.cu", "fdx_fused3d_grad.cu", "fdx_fused3d_curl.cu")
 NVCC_FLAGS = [
     *(["-DFDX_SWEEP"] if os.environ.get("FDX_SWEEP") else []),
+    *(["-DFDX_ABLATION"] if os.environ.get("FDX_ABLATION") else []),
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",

@@ -92,6 +92,7 @@ struct FusedParams {
   int z_lo, z_hi;      // addressable input planes [z_lo, z_hi]
   int halo_lo;         // tensor-map plane 0 is logical plane -halo_lo
   int chunk, n_chunks, tiles_x, tiles_y;
+  int ablate;  // FDX_SWEEP builds only: skip parts of the work to locate the bottleneck (results are wrong)
   short2 rng[kRowsMax];  // [first, last+1) nonzero band column of every band row
   T tab[kTabMax];
 };
@@ -228,7 +229,10 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   const int tile_x = b % prm.tiles_x;
   b /= prm.tiles_x;
   const int tile_y = b % prm.tiles_y;
-  const int chunk = b / prm.tiles_y;
+  // launch order: the two chunks that touch the physical z boundary go first -- their one-sided
+  // planes are slow and must not form the tail of the launch
+  const int cslot = b / prm.tiles_y;
+  const int chunk = cslot == 0 ? 0 : (cslot == 1 ? prm.n_chunks - 1 : cslot - 1);
   const int x0 = tile_x * G::TX, y0 = tile_y * G::TY;
   const int zs = prm.z_begin + chunk * prm.chunk;
   const int ze = min(prm.z_end, zs + prm.chunk);
@@ -272,15 +276,23 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   bool rok[RY];
 #pragma unroll
   for (int j = 0; j < RY; ++j) rok[j] = (xg < n2) && (yg + j < n1);
-  const bool yband = rok[0] && ((yg < A1.nl) || (yg + RY > n1 - A1.nr));
-  // CTA-uniform: does this tile touch the physical x boundary on the left / right?
-  const bool xedge_l = x0 < A2.nl;
-  const bool xedge_r = x0 + G::TX > n2 - A2.nr;
+#ifdef FDX_ABLATION
+  const bool no_bands = prm.ablate & 32;
+#define ABL(bit) (prm.ablate & (bit))
+#else
+  constexpr bool no_bands = false;
+#define ABL(bit) false
+#endif
+  const bool yband = !no_bands && !(ABL(128)) && rok[0] && ((yg < A1.nl) || (yg + RY > n1 - A1.nr));
+  // CTA-uniform: first / last tile along x (they hold the whole left / right band, host-checked)
+  const bool xedge_l = !no_bands && !(ABL(64)) && (tile_x == 0) && A2.nl > 0;
+  const bool xedge_r = !no_bands && !(ABL(64)) && (tile_x == prm.tiles_x - 1) && A2.nr > 0;
   const int64_t thread_ofs = (int64_t)yg * n2 + xg;  // this thread's first element inside a plane
-  // element offset of this thread's vector in tile row ty*RY of each field (constant per thread)
-  int toff[Tr::NIN];
+  // byte offset (from smem_raw, stage 0) of this thread's vector in tile row ty*RY of each field
+  uint32_t toffb[Tr::NIN];
 #pragma unroll
-  for (int f = 0; f < Tr::NIN; ++f) toff[f] = (ty * RY) * G::box_x(f) + G::xoff(f) + tx * V;
+  for (int f = 0; f < Tr::NIN; ++f)
+    toffb[f] = ring_off + G::field_off(f) + (uint32_t)sizeof(T) * ((ty * RY) * G::box_x(f) + G::xoff(f) + tx * V);
 
   VT acc[Tr::NACC][WZ][RY];
 #pragma unroll
@@ -293,13 +305,17 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
         for (int v = 0; v < V; ++v) acc[a][s][j].v[v] = 0;
 
   // ------------------------------------------------------------------ hot in-plane helpers
-  // D_y for output row j from centre rows c[j .. j+2P]
-  auto dy_main = [&](const VT* c, int j) {
-    VT r;
-    fma_vec<true>(r, A1.c[0], c[j]);
+  // D_y, streaming: centre row i of the RY+2P rows a thread sees feeds output rows j = i-2P .. i
+  // with tap i-j, so only one centre row is live at a time (keeps the register footprint small)
+  auto dy_feed = [&](VT (&ys)[RY], const VT& ci, int i) {  // i is a constant after unrolling
 #pragma unroll
-    for (int k = 1; k < WZ; ++k) fma_vec<false>(r, A1.c[k], c[j + k]);
-    return r;
+    for (int j = 0; j < RY; ++j) {
+      const int k = i - j;
+      if (k == 0)
+        fma_vec<true>(ys[j], A1.c[0], ci);
+      else if (k > 0 && k < WZ)
+        fma_vec<false>(ys[j], A1.c[k], ci);
+    }
   };
   // D_x for one row: `rowp` points at this thread's vector inside a tile row that has x halos
   auto dx_main = [&](const T* rowp, const VT& centre) {
@@ -340,138 +356,177 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   };
   // y band of global row y: taps from the tile when it holds all of them, else from global memory.
   // tcol: smem address of (tile row 0, this thread's x); gcol: global address of (z, row 0, xg)
+  // taps c in [c0, c1) in batches of four: all loads of a batch are issued before the first FMA, so
+  // a cold path costs about one load latency per batch instead of one per tap
+  auto band_dot_vec = [&](int tab, int c0, int c1, auto load /* (int c) -> VT */) {
+    VT a;
+#pragma unroll
+    for (int v = 0; v < V; ++v) a.v[v] = 0;
+    for (int c = c0; c < c1; c += 4) {
+      T cf[4];
+      VT x[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cc = min(c + q, c1 - 1);
+        cf[q] = prm.tab[tab + cc];
+        if (c + q >= c1) cf[q] = 0;
+        x[q] = load(cc);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v) a.v[v] = fma(cf[q], x[q].v[v], a.v[v]);
+    }
+    return a;
+  };
   auto band_y = [&](const T* tcol, int pitch, int boxy, const T* gcol, int y) {
     int tab, c0, c1, cb;
     band_rng(A1, y, tab, c0, c1, cb);
     VT a;
-#pragma unroll
-    for (int v = 0; v < V; ++v) a.v[v] = 0;
-    const int r0 = cb + c0 - (y0 - P);
-    if (r0 >= 0 && r0 + (c1 - c0) <= boxy) {
+    const int r0 = cb - (y0 - P);  // tile row of band column 0
+    if (r0 + c0 >= 0 && r0 + c1 <= boxy) {
       const T* p = tcol + r0 * pitch;
-      for (int c = c0; c < c1; ++c, p += pitch) {
-        const T cf = prm.tab[tab + c];
-        const VT x = *reinterpret_cast<const VT*>(p);
-#pragma unroll
-        for (int v = 0; v < V; ++v) a.v[v] = fma(cf, x.v[v], a.v[v]);
-      }
+      a = band_dot_vec(tab, c0, c1, [&](int c) { return *reinterpret_cast<const VT*>(p + c * pitch); });
     } else {
-      const T* p = gcol + (int64_t)(cb + c0) * n2;
-      for (int c = c0; c < c1; ++c, p += n2) {
-        const T cf = prm.tab[tab + c];
-        const VT x = ld_cached<T, V>(p);
-#pragma unroll
-        for (int v = 0; v < V; ++v) a.v[v] = fma(cf, x.v[v], a.v[v]);
-      }
+      const T* p = gcol + (int64_t)cb * n2;
+      a = band_dot_vec(tab, c0, c1, [&](int c) { return ld_cached<T, V>(p + (int64_t)c * n2); });
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) a.v[v] *= A1.alpha;
     return a;
   };
-  // x bands, warp-cooperative: lanes are re-mapped to (grid row of this warp, band vector) so that
-  // the few boundary columns of all WR rows of the warp are evaluated side by side from the tile in
-  // shared memory; results travel back to the owning lanes with shuffles.  `tilef` = tile of a field
-  // with x halos, `yo` its y halo offset, xs[] the per-row D_x vectors to patch.
-  auto xband_pass = [&](const T* tilef, int pitch, int yo, bool right, VT (&xs)[RY]) {
-    const int wrow0 = (tid / 32) * WR;  // first tile row of this warp
-    const int r = lane % WR, g = lane / WR;
-    // first owner vector (tile-relative) that intersects the band
-    const int v0 = right ? max(0, (n2 - A2.nr - x0) / V) : 0;
-    const int vx = v0 + g;  // owner vector handled by this lane
-    VT bv;
+  // x bands, warp-cooperative: the band outputs of the WR grid rows of this warp are spread over
+  // the lanes, one element each -- lane = r + WR * (side * NBS + ob) handles the ob-th band column
+  // of `side` (0 left, 1 right) in warp row r, reading the tile in shared memory; the results travel
+  // back to the owning lanes with shuffles.  The host guarantees that the first (last) tile holds
+  // every left (right) band output and all of its taps.
+  constexpr int NBS = (32 / WR) / 2;  // band columns per side and pass
+  // per owned element: 0x80 | band column index, packed one byte per vector element
+  uint32_t xb_desc = 0;
+  if (xedge_l || xedge_r) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) bv.v[v] = 0;
-    const int yrow = y0 + wrow0 + r;
-    if (vx < CFG::TXV && yrow < n1) {
-      const T* row = tilef + (wrow0 + r + yo) * pitch;  // tile column 0 <-> global x0 - HX
+    for (int v = 0; v < V; ++v) {
+      const int x = xg + v;
+      uint32_t d = 0;
+      if (xedge_l && x < A2.nl) d = 0x80u | (uint32_t)x;
+      if (xedge_r && x >= n2 - A2.nr && x < n2) d = 0xC0u | (uint32_t)(x - (n2 - A2.nr));  // 0x40: right side
+      xb_desc |= d << (8 * v);
+    }
+  }
+  auto xband_fix = [&](const T* tilef, int pitch, int yo, VT (&xs)[RY]) {
+    const int wrow0 = (tid / 32) * WR;  // first tile row of this warp
+    const int r = lane % WR, slot = lane / WR;
+    const int side = slot / NBS, obl = slot % NBS;
+    const int nb = side ? (xedge_r ? A2.nr : 0) : (xedge_l ? A2.nl : 0);
+    const int nbmax = max(xedge_l ? A2.nl : 0, xedge_r ? A2.nr : 0);
+    const T* src0 = tilef + (wrow0 + r + yo) * pitch - (x0 - HX);  // address of global column 0 of this row
+    const bool row_in = y0 + wrow0 + r < n1;
+    const int myrow = (ty % TRW) * RY;
+    for (int ob0 = 0; ob0 < nbmax; ob0 += NBS) {  // one pass unless a band is wider than NBS
+      const int ob = ob0 + obl;
+      T val = 0;
+      if (ob < nb && row_in) {
+        const int x = side ? (n2 - A2.nr + ob) : ob;
+        int tab, c0, c1, cb;
+        band_rng(A2, x, tab, c0, c1, cb);
+        const T* src = src0 + cb;
+        T a = 0;
+        for (int c = c0; c < c1; c += 4) {
+          T cf[4], xv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int cc = min(c + q, c1 - 1);
+            cf[q] = prm.tab[tab + cc];
+            if (c + q >= c1) cf[q] = 0;
+            xv[q] = src[cc];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a = fma(cf[q], xv[q], a);
+        }
+        val = a * A2.alpha;
+      }
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const int x = x0 + vx * V + v;
-        if (x < n2 && (right ? x >= n2 - A2.nr : x < A2.nl)) {
-          int tab, c0, c1, cb;
-          band_rng(A2, x, tab, c0, c1, cb);
-          const int s0 = cb - (x0 - HX);
-          T a = 0;
-          for (int c = c0; c < c1; ++c) a = fma(prm.tab[tab + c], row[s0 + c], a);
-          bv.v[v] = a * A2.alpha;
+        const uint32_t d = (xb_desc >> (8 * v)) & 0xffu;
+        const int obx = (int)(d & 0x3fu) - ob0;
+        const bool mine = (d & 0x80u) && obx >= 0 && obx < NBS;
+        const int col = WR * (((d & 0x40u) ? NBS : 0) + (mine ? obx : 0));
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          const T got = __shfl_sync(0xffffffffu, val, (myrow + j + col) & 31);
+          if (mine) xs[j].v[v] = got;
         }
       }
     }
-    // deliver to the owners: the thread (tx, ty) owns vector tx of rows ty*RY + j
-    const int gsrc = tx - v0;
-    const int trow = (ty % TRW) * RY;
-#pragma unroll
-    for (int j = 0; j < RY; ++j) {
-      const int src = (gsrc >= 0 ? gsrc : 0) * WR + trow + j;
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const T got = __shfl_sync(0xffffffffu, bv.v[v], src & 31);
-        const int x = xg + v;
-        if (gsrc >= 0 && (right ? (x >= n2 - A2.nr) : (x < A2.nl))) xs[j].v[v] = got;
-      }
-    }
-  };
-  auto xband_fix = [&](const T* tilef, int pitch, int yo, VT (&xs)[RY]) {
-    if (xedge_l) xband_pass(tilef, pitch, yo, false, xs);
-    if (xedge_r) xband_pass(tilef, pitch, yo, true, xs);
   };
   // z band of plane z (always from global memory: the other planes are not in the ring)
   auto band_z = [&](const T* gcol0 /* global address of (plane 0, this row, xg) */, int z) {
     int tab, c0, c1, cb;
     band_rng(A0, z, tab, c0, c1, cb);
-    VT a;
-#pragma unroll
-    for (int v = 0; v < V; ++v) a.v[v] = 0;
-    const T* p = gcol0 + (int64_t)(cb + c0) * plane;
-#pragma unroll 2
-    for (int c = c0; c < c1; ++c, p += plane) {
-      const T cf = prm.tab[tab + c];
-      const VT x = ld_cached<T, V>(p);
-#pragma unroll
-      for (int v = 0; v < V; ++v) a.v[v] = fma(cf, x.v[v], a.v[v]);
-    }
+    const T* p = gcol0 + (int64_t)cb * plane;
+    VT a = band_dot_vec(tab, c0, c1, [&](int c) { return ld_cached<T, V>(p + (int64_t)c * plane); });
 #pragma unroll
     for (int v = 0; v < V; ++v) a.v[v] *= A0.alpha;
     return a;
   };
-  auto zband = [&](int z) { return z < A0.nl || z >= n0 - A0.nr; };
+  auto zband = [&](int z) { return !no_bands && !(ABL(256)) && (z < A0.nl || z >= n0 - A0.nr); };
   auto is_yband = [&](int j) { return rok[j] && (yg + j < A1.nl || yg + j >= n1 - A1.nr); };
   auto store = [&](int o, int z, int j, const VT& val) {
+#ifdef FDX_ABLATION
+    if (prm.ablate & 8) return;
+#endif
     if (rok[j]) st_vec<T, V>(prm.out[o] + (int64_t)z * plane + thread_ofs + (int64_t)j * n2, val);
   };
 
   // ---- march along z ---------------------------------------------------------------------
-  int u = 0;  // it % WZ
-  for (int it = 0; it < n_planes; ++it) {
-    const int zc = zin0 + it;
-    const int s = it % STAGES;
-    const bool inr = (zc >= zs) && (zc < ze);  // this plane is also an output plane of ours
+  int u = 0;                // it % WZ   (phase of the register queue)
+  int stage = 0;            // it % STAGES
+  uint32_t stage_off = 0;   // stage * STAGE_BYTES
+  uint32_t full_parity = 0;
+  int zc = zin0;
+  for (int it = 0; it < n_planes; ++it, ++zc) {
+    const bool inr = (unsigned)(zc - zs) < (unsigned)(ze - zs);  // this plane is also an output plane of ours
     const bool zb = inr && zband(zc);
     // keep STAGES-1 planes in flight: the stage consumed at step it-1 is refilled now
     if (tid == 0 && it + STAGES - 1 < n_planes) issue(it + STAGES - 1);
-    mbar_wait(&full_bar[s], (it / STAGES) & 1);
-    const unsigned char* st = smem_raw + ring_off + (size_t)s * G::STAGE_BYTES;
-    auto tile = [&](int f) { return reinterpret_cast<const T*>(st + G::field_off(f)); };
+    mbar_wait(&full_bar[stage], full_parity);
+    auto tile = [&](int f) { return reinterpret_cast<const T*>(smem_raw + ring_off + stage_off + G::field_off(f)); };
     // address of this thread's vector in tile row (ty*RY + i) of field f
-    auto tptr = [&](int f, int i) { return tile(f) + toff[f] + i * G::box_x(f); };
+    auto tptr = [&](int f, int i) {
+      return reinterpret_cast<const T*>(smem_raw + stage_off + toffb[f]) + i * G::box_x(f);
+    };
     const int64_t zofs = (int64_t)zc * plane;
 
     VT zv[Tr::NACC][RY];   // values scattered along z
     VT tin[Tr::NACC][RY];  // in-plane contribution to plane zc of each accumulator set
     // ---------------- in-plane part (one copy of this code: it does not depend on the queue phase)
     if constexpr (OP == LAP || OP == GRAD) {
-      VT c[RY + 2 * P];
+      VT ys[RY], xs[RY];
 #pragma unroll
-      for (int i = 0; i < RY + 2 * P; ++i) c[i] = *reinterpret_cast<const VT*>(tptr(0, i));
+      for (int i = 0; i < RY + 2 * P; ++i) {
+#ifdef FDX_ABLATION
+        VT ci;
+        if (prm.ablate & 16) {
 #pragma unroll
-      for (int j = 0; j < RY; ++j) zv[0][j] = c[j + P];
-      if (inr) {
-        VT ys[RY], xs[RY];
-#pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          ys[j] = dy_main(c, j);
-          xs[j] = dx_main(tptr(0, j + P), c[j + P]);
+          for (int v = 0; v < V; ++v) ci.v[v] = (T)1;
+        } else {
+          ci = *reinterpret_cast<const VT*>(tptr(0, i));
         }
+        if (inr && !(prm.ablate & 2)) dy_feed(ys, ci, i);
+        if (i >= P && i < P + RY) {
+          zv[0][i - P] = ci;
+          if (inr && !(prm.ablate & 1)) xs[i - P] = dx_main(tptr(0, i), ci);
+        }
+#else
+        const VT ci = *reinterpret_cast<const VT*>(tptr(0, i));
+        if (inr) dy_feed(ys, ci, i);
+        if (i >= P && i < P + RY) {
+          zv[0][i - P] = ci;
+          if (inr) xs[i - P] = dx_main(tptr(0, i), ci);
+        }
+#endif
+      }
+      if (inr) {
         if (yband) {
 #pragma unroll
           for (int j = 0; j < RY; ++j)
@@ -493,13 +548,11 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 #pragma unroll
       for (int j = 0; j < RY; ++j) zv[0][j] = *reinterpret_cast<const VT*>(tptr(0, j));
       if (inr) {
-        VT c[RY + 2 * P];
-#pragma unroll
-        for (int i = 0; i < RY + 2 * P; ++i) c[i] = *reinterpret_cast<const VT*>(tptr(1, i));
         VT ys[RY], xs[RY];
 #pragma unroll
+        for (int i = 0; i < RY + 2 * P; ++i) dy_feed(ys, *reinterpret_cast<const VT*>(tptr(1, i)), i);
+#pragma unroll
         for (int j = 0; j < RY; ++j) {
-          ys[j] = dy_main(c, j);
           const VT ctr = *reinterpret_cast<const VT*>(tptr(2, j));
           xs[j] = dx_main(tptr(2, j), ctr);
         }
@@ -517,26 +570,24 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       }
     } else {  // CURL
       // out_0 = D1 x2 - D2 x1 ; out_1 = D2 x0 - D0 x2 (acc set 0) ; out_2 = D0 x1 - D1 x0 (acc set 1)
-      VT c2[RY + 2 * P];
+      VT y2[RY], x1[RY], y0v[RY], x0v[RY];
 #pragma unroll
-      for (int i = 0; i < RY + 2 * P; ++i) c2[i] = *reinterpret_cast<const VT*>(tptr(2, i));
-#pragma unroll
-      for (int j = 0; j < RY; ++j) {
-        zv[0][j] = c2[j + P];                                  // x2 -> -D0 x2 into out_1
-        zv[1][j] = *reinterpret_cast<const VT*>(tptr(1, j));    // x1 -> +D0 x1 into out_2
+      for (int i = 0; i < RY + 2 * P; ++i) {
+        const VT ci = *reinterpret_cast<const VT*>(tptr(2, i));
+        if (inr) dy_feed(y2, ci, i);                  // D1 x2
+        if (i >= P && i < P + RY) zv[0][i - P] = ci;  // x2 -> -D0 x2 into out_1
       }
+#pragma unroll
+      for (int j = 0; j < RY; ++j) zv[1][j] = *reinterpret_cast<const VT*>(tptr(1, j));  // x1 -> +D0 x1 into out_2
       if (inr) {
-        VT c0[RY + 2 * P];
 #pragma unroll
-        for (int i = 0; i < RY + 2 * P; ++i) c0[i] = *reinterpret_cast<const VT*>(tptr(0, i));
-        VT y2[RY], x1[RY], y0v[RY], x0v[RY];
-#pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          y2[j] = dy_main(c2, j);                          // D1 x2
-          x1[j] = dx_main(tptr(1, j), zv[1][j]);           // D2 x1
-          y0v[j] = dy_main(c0, j);                         // D1 x0
-          x0v[j] = dx_main(tptr(0, j + P), c0[j + P]);     // D2 x0
+        for (int i = 0; i < RY + 2 * P; ++i) {
+          const VT ci = *reinterpret_cast<const VT*>(tptr(0, i));
+          dy_feed(y0v, ci, i);                                              // D1 x0
+          if (i >= P && i < P + RY) x0v[i - P] = dx_main(tptr(0, i), ci);  // D2 x0
         }
+#pragma unroll
+        for (int j = 0; j < RY; ++j) x1[j] = dx_main(tptr(1, j), zv[1][j]);  // D2 x1
         if (yband) {
 #pragma unroll
           for (int j = 0; j < RY; ++j)
@@ -564,7 +615,12 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     }
     // this warp no longer reads the stage: release it (one arrive per warp)
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == STAGES) {
+      stage = 0, stage_off = 0, full_parity ^= 1u;
+    } else {
+      stage_off += G::STAGE_BYTES;
+    }
 
     // ---------------- planes next to a physical z boundary: one-sided taps, gathered directly
     if (zb) {
@@ -597,6 +653,12 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     // plane zc feeds output z' = zc + P - k with tap k; slot(z') = (it - k) mod WZ
     auto phase = [&](auto U_) {
       constexpr int U = decltype(U_)::value;
+#ifdef FDX_ABLATION
+      if (prm.ablate & 4) {
+        if (emit) store(0, zo, 0, zv[0][0]);
+        return;
+      }
+#endif
 #pragma unroll
       for (int a = 0; a < Tr::NACC; ++a) {
 #pragma unroll
@@ -735,6 +797,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     }
   }
   prm.z_begin = sl.z_begin, prm.z_end = sl.z_end;
+  prm.ablate = env_int("FDX_ABLATE", 0);
   prm.halo_lo = sl.halo_lo;
   prm.z_lo = -sl.halo_lo, prm.z_hi = n0 - 1 + sl.halo_hi;
   for (int f = 0; f < Tr::NIN; ++f) {
@@ -744,16 +807,24 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
   }
   prm.tiles_x = (n2 + G::TX - 1) / G::TX;
   prm.tiles_y = (n1 + G::TY - 1) / G::TY;
+  {
+    // the x bands are evaluated from the first / last tile in shared memory: those tiles must hold
+    // every band output of their side and all of its taps (otherwise: composition fallback)
+    const fdx_plan_s* px = plans[2];
+    const int xl = (prm.tiles_x - 1) * G::TX;
+    if (px->nl > G::TX || px->wl > G::TX + G::HX || n2 - xl < px->nr || xl > n2 - px->wr + G::HX) return FDX_EUNSUPPORTED;
+    if (px->nl > 63 || px->nr > 63) return FDX_EUNSUPPORTED;
+  }
   const int nz = sl.z_end - sl.z_begin;
   const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
   // z chunking: enough CTAs for a few waves, but chunks long enough to amortise the 2P warm-up planes
+  // z chunking: many short CTAs beat few long ones on B200 (dynamic scheduling hides the slow
+  // boundary tiles); 32 planes amortise the 2P warm-up planes of every chunk well enough
   int chunk = env_int("FDX_FUSED_CHUNK", 0);
   if (chunk <= 0) {
-    const int64_t want = (int64_t)kNumSMs * 6;
-    int64_t nch = (want + tiles - 1) / tiles;
-    chunk = (int)((nz + nch - 1) / nch);
-    const int min_chunk = 16 * P;
-    if (chunk < min_chunk) chunk = min_chunk;
+    chunk = 32 > 8 * P ? 32 : 8 * P;
+    // small grids: keep at least ~2 waves of CTAs
+    while (chunk > 4 * P && tiles * ((nz + chunk - 1) / chunk) < 2LL * kNumSMs * CFG::MINB) chunk /= 2;
   }
   if (chunk > nz) chunk = nz;
   prm.chunk = chunk;
@@ -790,24 +861,30 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
       FDX_CFG(8, 16, 16, 2, 6, 1)
       FDX_CFG(9, 16, 8, 2, 4, 4)
       FDX_CFG(10, 16, 8, 4, 4, 2)
-      FDX_CFG(11, 16, 16, 2, 3, 3)
+      FDX_CFG(11, 16, 8, 2, 4, 3)
+      FDX_CFG(12, 16, 16, 2, 6, 2)
+      FDX_CFG(13, 16, 8, 2, 6, 4)
+      FDX_CFG(14, 32, 8, 2, 6, 2)
+      FDX_CFG(15, 16, 8, 2, 8, 3)
       default:
         break;
     }
   }
 #endif
+  // defaults from the round-1 sweeps on B200 (tools/sweep_fused.py, profiles/): 64x16-point tiles,
+  // 128 threads, 8 TMA stages, 3 CTAs per SM for the light operators
   constexpr bool heavy = (OP == CURL) || (sizeof(T) == 8 && P >= 3);
   if constexpr (heavy) {
     switch (cfg) {
-      FDX_CFG(1, 16, 16, 1, 4, 2)
+      FDX_CFG(1, 16, 16, 1, 4, 1)
       default:
-        return launch_cfg<OP, T, P, Cfg<16, 16, 1, 4, 1>>(plans, in, out, alpha, sl, st);
+        return launch_cfg<OP, T, P, Cfg<16, 16, 1, 4, 2>>(plans, in, out, alpha, sl, st);
     }
   } else {
     switch (cfg) {
-      FDX_CFG(1, 16, 16, 2, 4, 1)
+      FDX_CFG(1, 16, 16, 2, 4, 2)
       default:
-        return launch_cfg<OP, T, P, Cfg<16, 16, 2, 4, 2>>(plans, in, out, alpha, sl, st);
+        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 8, 3>>(plans, in, out, alpha, sl, st);
     }
   }
 #undef FDX_CFG
