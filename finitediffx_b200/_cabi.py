@@ -47,7 +47,13 @@ class _AxisDesc(C.Structure):
 
 
 class Slab(C.Structure):
-    _fields_ = [("z_begin", C.c_int32), ("z_end", C.c_int32), ("halo_lo", C.c_int32), ("halo_hi", C.c_int32)]
+    _fields_ = [
+        ("z_begin", C.c_int32),
+        ("z_end", C.c_int32),
+        ("in_first", C.c_int32),
+        ("in_planes", C.c_int32),
+        ("out_first", C.c_int32),
+    ]
 
 
 EXPORTS = (
@@ -249,4 +255,39 @@ def fused3d(kind: str, plans: Sequence[AxisPlan], xs, outs, alpha: Sequence[floa
     if rc == -2:  # FDX_EUNSUPPORTED
         return rc
     check(rc, f"fdx_{kind}3d")
+    return 0
+
+
+def fused3d_ptr(kind: str, plans: Sequence[AxisPlan], in_ptrs: Sequence[int], out_ptrs: Sequence[int], alpha: Sequence[float],
+                dtype: torch.dtype, device: torch.device, z_begin: int, z_end: int, in_first: int, in_planes: int,
+                out_first: int, stream: "torch.cuda.Stream | None" = None) -> int:
+    """Raw-pointer form of the fused 3-D entry points for slab execution (multi-GPU halos, host
+    streaming).  The plans describe the global grid; ``in_ptrs`` designate global plane ``in_first``
+    of buffers holding ``in_planes`` planes, ``out_ptrs`` global plane ``out_first`` (see fdx_slab in
+    include/fdx_b200.h).  Returns the library status (0, or -2 = unsupported by the fused kernels)."""
+    keep, hp = _handles(plans, device)
+    sfx = "f32" if dtype == torch.float32 else "f64"
+    st = C.c_void_p((stream or torch.cuda.current_stream(device)).cuda_stream)
+    slab = Slab(int(z_begin), int(z_end), int(in_first), int(in_planes), int(out_first))
+    lib = load()
+
+    def arr(ptrs):
+        ptrs = list(ptrs) + [0] * (3 - len(ptrs))
+        return (C.c_void_p * 3)(*[C.c_void_p(int(p)) for p in ptrs])
+
+    with torch.cuda.device(device):
+        if kind == "laplacian":
+            rc = getattr(lib, f"fdx_laplacian3d_{sfx}")(hp, C.c_void_p(int(in_ptrs[0])), C.c_void_p(int(out_ptrs[0])), _alphas(alpha), C.byref(slab), st)
+        elif kind == "divergence":
+            rc = getattr(lib, f"fdx_divergence3d_{sfx}")(hp, arr(in_ptrs), C.c_void_p(int(out_ptrs[0])), _alphas(alpha), C.byref(slab), st)
+        elif kind == "gradient":
+            rc = getattr(lib, f"fdx_gradient3d_{sfx}")(hp, C.c_void_p(int(in_ptrs[0])), arr(out_ptrs), _alphas(alpha), C.byref(slab), st)
+        elif kind == "curl":
+            rc = getattr(lib, f"fdx_curl3d_{sfx}")(hp, arr(in_ptrs), arr(out_ptrs), _alphas(alpha), C.byref(slab), st)
+        else:
+            raise ValueError(kind)
+    del keep
+    if rc == -2:
+        return rc
+    check(rc, f"fdx_{kind}3d (slab)")
     return 0

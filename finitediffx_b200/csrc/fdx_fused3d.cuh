@@ -17,7 +17,8 @@
 //   * rows/columns/planes next to a physical boundary use the plan's dense band taps (the
 //     reference's one-sided stencils or their transposes): those few points re-gather their taps
 //     from global memory (L2-resident, the planes were just streamed).
-//   * multi-GPU slabs: with halo_lo/halo_hi the z march simply starts in the halo planes.
+//   * slabs (multi-GPU halos, host streaming): the buffers hold a window of planes of the global grid;
+//     plane indices stay global, so the boundary logic is the single-GPU one.
 //
 // Anything this kernel does not cover (non-central plans, mixed radii, unaligned shapes) falls
 // back -- inside the library, still on the GPU -- to the composition of axis kernels.
@@ -90,7 +91,7 @@ struct FusedParams {
   AxisDev<T> ax[3];
   int z_begin, z_end;  // output planes
   int z_lo, z_hi;      // addressable input planes [z_lo, z_hi]
-  int halo_lo;         // tensor-map plane 0 is logical plane -halo_lo
+  int tz_off;          // tensor-map plane index = global plane index + tz_off (= -in_first)
   int chunk, n_chunks, tiles_x, tiles_y;
   int ablate;  // FDX_SWEEP builds only: skip parts of the work to locate the bottleneck (results are wrong)
   short2 rng[kRowsMax];  // [first, last+1) nonzero band column of every band row
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);  // all warps released it
     mbar_expect_tx(&full_bar[s], G::tx_bytes());
     unsigned char* dst = smem_raw + ring_off + (size_t)s * G::STAGE_BYTES;
-    const int zc = zin0 + it + prm.halo_lo;
+    const int zc = zin0 + it + prm.tz_off;
 #pragma unroll
     for (int f = 0; f < Tr::NIN; ++f)
       tma_load_3d(dst + G::field_off(f), &prm.tmap[f], &full_bar[s], x0 - G::xoff(f), y0 - G::yoff(f), zc);
@@ -748,12 +749,12 @@ static int env_int(const char* name, int dflt) {
 }
 
 struct SlabArgs {
-  int z_begin, z_end, halo_lo, halo_hi;
+  int z_begin, z_end, in_first, in_planes, out_first;
 };
 
 static SlabArgs slab_args(const fdx_plan_t plans[3], const fdx_slab* s) {
-  if (!s) return SlabArgs{0, plans[0]->n, 0, 0};
-  return SlabArgs{s->z_begin, s->z_end, s->halo_lo, s->halo_hi};
+  if (!s) return SlabArgs{0, plans[0]->n, 0, plans[0]->n, 0};
+  return SlabArgs{s->z_begin, s->z_end, s->in_first, s->in_planes, s->out_first};
 }
 
 template <Op OP, typename T, int P, typename CFG>
@@ -763,9 +764,12 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
   using Tr = OpTraits<OP>;
   const int n0 = plans[0]->n, n1 = plans[1]->n, n2 = plans[2]->n;
   FusedParams<T> prm;
+  // plain loads/stores address planes by their global index through pointers to (virtual) plane 0;
+  // only addresses inside the caller's window are ever dereferenced.  TMA gets the real base.
+  const int64_t plane_elems = (int64_t)n1 * n2;
   for (int f = 0; f < 3; ++f) {
-    prm.in[f] = f < Tr::NIN ? in[f] : nullptr;
-    prm.out[f] = f < Tr::NOUT ? out[f] : nullptr;
+    prm.in[f] = f < Tr::NIN ? in[f] - (int64_t)sl.in_first * plane_elems : nullptr;
+    prm.out[f] = f < Tr::NOUT ? out[f] - (int64_t)sl.out_first * plane_elems : nullptr;
   }
   int tab_used = 0, rows_used = 0;
   for (int k = 0; k < 3; ++k) {
@@ -798,11 +802,10 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
   }
   prm.z_begin = sl.z_begin, prm.z_end = sl.z_end;
   prm.ablate = env_int("FDX_ABLATE", 0);
-  prm.halo_lo = sl.halo_lo;
-  prm.z_lo = -sl.halo_lo, prm.z_hi = n0 - 1 + sl.halo_hi;
+  prm.tz_off = -sl.in_first;
+  prm.z_lo = 0, prm.z_hi = n0 - 1;
   for (int f = 0; f < Tr::NIN; ++f) {
-    int rc = make_tmap<T>(&prm.tmap[f], in[f] - (int64_t)sl.halo_lo * n1 * n2, n2, n1, (int64_t)n0 + sl.halo_lo + sl.halo_hi,
-                          G::box_x(f), G::box_y(f));
+    int rc = make_tmap<T>(&prm.tmap[f], in[f], n2, n1, (int64_t)sl.in_planes, G::box_x(f), G::box_y(f));
     if (rc) return rc;
   }
   prm.tiles_x = (n2 + G::TX - 1) / G::TX;
@@ -905,14 +908,23 @@ static int fused_radius(const fdx_plan_t plans[3], const T* const in[3], T* cons
     if (p->nl + p->nr > p->n) return 0;                 // dense (tiny-n) plans
     if (p->n < 1) return 0;
   }
-  if (plans[0]->nl == 0 ? sl.halo_lo < P : plans[0]->nl < P) return 0;
-  if (plans[0]->nr == 0 ? sl.halo_hi < P : plans[0]->nr < P) return 0;
+  if (plans[0]->nl < P || plans[0]->nr < P) return 0;
   if (plans[2]->n % V != 0) return 0;
   for (int f = 0; f < Tr::NIN; ++f)
     if (((uintptr_t)in[f] & 15) != 0) return 0;
   for (int f = 0; f < Tr::NOUT; ++f)
     if (((uintptr_t)out[f] & 15) != 0) return 0;
   if (sl.z_begin < 0 || sl.z_end > plans[0]->n || sl.z_begin >= sl.z_end) return 0;
+  {
+    // the planes this call reads must lie inside the caller's window
+    const fdx_plan_s* p0 = plans[0];
+    int lo = sl.z_begin - P < 0 ? 0 : sl.z_begin - P;
+    int hi = sl.z_end + P > p0->n ? p0->n : sl.z_end + P;
+    if (sl.z_begin < p0->nl) lo = 0, hi = hi > p0->wl ? hi : p0->wl;
+    if (sl.z_end > p0->n - p0->nr) lo = lo < p0->n - p0->wr ? lo : p0->n - p0->wr, hi = p0->n;
+    if (lo < sl.in_first || hi > sl.in_first + sl.in_planes) return -1;
+    if (sl.z_begin < sl.out_first) return -1;
+  }
   if (!encode_fn()) return 0;
   return P;
 }
@@ -967,6 +979,7 @@ static int run(const fdx_plan_t plans[3], const T* const in[3], T* const out[3],
   if (plans[0]->n == 0 || plans[1]->n == 0 || plans[2]->n == 0) return FDX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = fused_radius<OP, T>(plans, in, out, sl);
+  if (P < 0) return FDX_EINVAL;
   int rc = FDX_EUNSUPPORTED;
   switch (P) {
     case 1:
@@ -986,8 +999,7 @@ static int run(const fdx_plan_t plans[3], const T* const in[3], T* const out[3],
   }
   if (rc != FDX_EUNSUPPORTED) return rc;
   // fallback: only the whole-grid, no-halo form can be composed from the axis kernels
-  if (sl.z_begin != 0 || sl.z_end != plans[0]->n || sl.halo_lo != 0 || sl.halo_hi != 0) return FDX_EUNSUPPORTED;
-  if (plans[0]->nl + plans[0]->nr == 0 && plans[0]->lo != plans[0]->hi) return FDX_EUNSUPPORTED;
+  if (sl.z_begin != 0 || sl.z_end != plans[0]->n || sl.in_first != 0 || sl.out_first != 0) return FDX_EUNSUPPORTED;
   return composed<OP, T>(plans, in, out, alpha, stream);
 }
 

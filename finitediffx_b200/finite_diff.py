@@ -147,19 +147,77 @@ def _to_device(array):
     # output dtype rule (reference: promote(coefficients, input)): float64 stays float64,
     # everything else (float32, half, bfloat16, integers, bool) computes in float32
     target = torch.float64 if t.dtype == torch.float64 else torch.float32
-    src_device = t.device
+    pinned = (not t.is_cuda) and t.is_pinned()
     if not t.is_cuda:
-        t = t.to("cuda", non_blocking=False)
+        t = t.to("cuda", non_blocking=pinned)
     t = t.to(target).contiguous()
 
     def restore(r: torch.Tensor):
         if kind == "cuda":
             return r
-        if kind == "cpu":
-            return r.to(src_device)
-        return r.cpu().numpy()
+        host = torch.empty(r.shape, dtype=r.dtype, pin_memory=True)  # torch caches pinned blocks
+        host.copy_(r, non_blocking=True)
+        torch.cuda.current_stream(r.device).synchronize()
+        return host if kind == "cpu" else host.numpy()
 
     return t, restore
+
+
+# ------------------------------------------------------------------ host arrays: streamed slabs
+_streamers: dict = {}
+
+
+def _host_streamed(kind: str, array, accuracy, step_size, method: str, n_out: int):
+    """Large host-resident 3-D grids: pipeline slabs through the GPU (H2D, kernel, D2H overlapped,
+    finitediffx_b200/slab.py) instead of staging the whole array in HBM.  Returns None when the
+    call is not of that kind, so that the caller takes the ordinary path."""
+    from . import slab as _slab
+
+    if isinstance(array, torch.Tensor):
+        if array.is_cuda or array.requires_grad:
+            return None
+        t, as_numpy = array, False
+    elif isinstance(array, np.ndarray):
+        t, as_numpy = torch.from_numpy(np.ascontiguousarray(array)), True
+    else:
+        return None
+    nin = _slab.FIELDS[kind][0]
+    if t.dtype not in (torch.float32, torch.float64) or not torch.cuda.is_available():
+        return None
+    if t.ndim != (3 if nin == 1 else 4) or (nin == 3 and t.shape[0] != 3):
+        return None
+    spatial = tuple(t.shape[-3:])
+    if t.numel() < (1 << 24):  # small grids: one copy each way is simpler and as fast
+        return None
+    acc = _check_and_return(accuracy, 3, "accuracy")
+    steps = _check_and_return(step_size, 3, "step_size")
+    if len(set(acc)) != 1 or method != "central":
+        return None
+    dev = torch.device("cuda", torch.cuda.current_device())
+    try:
+        spec = _slab.make_spec(kind, spatial, accuracy=acc[0], step_size=tuple(steps), method=method)
+    except ValueError:
+        return None
+    key = (kind, spatial, t.dtype, acc[0], tuple(float(h) for h in steps), dev.index, _slab.DEFAULT_SLAB_BYTES)
+    st = _streamers.get(key)
+    if st is None:
+        if len(_streamers) > 4:
+            _streamers.clear()
+        st = _streamers[key] = _slab.HostStreamer(spec, t.dtype, dev, slab_planes=max(8, _slab.DEFAULT_SLAB_BYTES // max(1, spatial[1] * spatial[2] * t.element_size())))
+    t = t.contiguous()
+    if not t.is_pinned():
+        pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        pinned.copy_(t)
+        t = pinned
+    out = torch.empty(((n_out,) if n_out > 1 else ()) + spatial, dtype=t.dtype, pin_memory=True)
+    xs = [t] if nin == 1 else [t[0], t[1], t[2]]
+    outs = [out] if n_out == 1 else [out[k] for k in range(n_out)]
+    try:
+        st.run(xs, outs)
+    except _cabi.FdxError:
+        return None
+    torch.cuda.current_stream(dev).synchronize()
+    return out.numpy() if as_numpy else out
 
 
 def _alpha(step, derivative: int) -> float:
@@ -221,6 +279,9 @@ def gradient(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
 
     Drop-in for the reference's ``gradient`` (finite_diff.py:300-351).  Index notation: dF/dxi
     """
+    streamed = _host_streamed("gradient", array, accuracy, step_size, method, 3)
+    if streamed is not None:
+        return streamed
     x, restore = _to_device(array)
     accuracy = _check_and_return(accuracy, x.ndim, "accuracy")
     step_size = _check_and_return(step_size, x.ndim, "step_size")
@@ -253,6 +314,9 @@ def divergence(array, *, accuracy=1, step_size=1, keepdims: bool = True, method:
 
     Drop-in for the reference's ``divergence`` (finite_diff.py:404-457).  Index notation: dFi/dxi
     """
+    streamed = _host_streamed("divergence", array, accuracy, step_size, method, 1)
+    if streamed is not None:
+        return streamed[None] if keepdims else streamed
     x, restore = _to_device(array)
     nd = x.ndim - 1
     accuracy = _check_and_return(accuracy, nd, "accuracy")
@@ -293,6 +357,9 @@ def laplacian(array, *, accuracy=1, step_size=1, method: MethodKind = "central")
 
     Drop-in for the reference's ``laplacian`` (finite_diff.py:532-575).
     """
+    streamed = _host_streamed("laplacian", array, accuracy, step_size, method, 1)
+    if streamed is not None:
+        return streamed
     x, restore = _to_device(array)
     accuracy = _check_and_return(accuracy, x.ndim, "accuracy")
     step_size = _check_and_return(step_size, x.ndim, "step_size")
@@ -307,6 +374,9 @@ def curl(array, *, accuracy=1, step_size=1, method: MethodKind = "central", keep
     Drop-in for the reference's ``curl`` (finite_diff.py:671-741): 3-D fields need shape (3, ...)
     (``keepdims`` ignored, as there), 2-D fields shape (2, ...); anything else raises ``ValueError``.
     """
+    streamed = _host_streamed("curl", array, accuracy, step_size, method, 3)
+    if streamed is not None:
+        return streamed
     x, restore = _to_device(array)
     nd = x.ndim - 1
     accuracy = _check_and_return(accuracy, nd, "accuracy")

@@ -74,15 +74,20 @@ int fdx_axis_apply_f64(fdx_plan_t plan, const double* x, double* out, int64_t ou
 /* ---- fused 3-D operators on a C-contiguous (n0, n1, n2) grid; plans[k] acts along axis k and
  * plans[k]->n == n_k.  One pass: every input plane is read once, every output written once.
  *
- * Slab arguments (multi-GPU halo exchange along axis 0, single GPU passes the defaults):
- *   z_begin,z_end : only output planes [z_begin, z_end) are computed/written (default 0, n0);
- *   halo_lo,halo_hi : planes [-halo_lo, n0+halo_hi) of every INPUT are addressable around the
- *                     logical origin the pointer designates (default 0, 0).  A plan with nl == 0
- *                     (nr == 0) along axis 0 reads its lower (upper) halo instead of using a
- *                     boundary band.                                                         */
+ * Slab arguments (multi-GPU halo exchange or host streaming along axis 0; NULL = the whole grid):
+ * the plans describe the GLOBAL grid (plans[0]->n global planes); the caller's buffers hold only a
+ * window of planes:
+ *   z_begin,z_end      : output planes [z_begin, z_end) (global indices) are computed and written;
+ *   in_first,in_planes : every INPUT pointer designates global plane in_first and in_planes planes
+ *                        are addressable behind it.  The call reads planes [z_begin-P, z_end+P)
+ *                        clipped to the grid (P = stencil radius) and, when the range touches a
+ *                        physical boundary, the planes under the one-sided boundary stencils;
+ *                        all of them must lie inside the window (FDX_EINVAL otherwise);
+ *   out_first          : every OUTPUT pointer designates global plane out_first.               */
 typedef struct {
   int32_t z_begin, z_end;
-  int32_t halo_lo, halo_hi;
+  int32_t in_first, in_planes;
+  int32_t out_first;
 } fdx_slab;
 
 /* laplacian (finite_diff.py:532-575):  out = sum_k alpha[k] * D_k x                         */
