@@ -175,6 +175,24 @@ def _stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _on_device:
+    """`with torch.cuda.device(d)` only when d is not already current (the common case is free)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        idx = device.index
+        self.ctx = None if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 def _sfx(t: torch.Tensor) -> str:
     if t.dtype == torch.float32:
         return "f32"
@@ -202,7 +220,7 @@ def axis_apply(plan: AxisPlan, x: torch.Tensor, out: torch.Tensor, axis: int, al
     outer = int(np.prod(shape[:axis], dtype=np.int64)) if axis > 0 else 1
     inner = int(np.prod(shape[axis + 1 :], dtype=np.int64)) if axis + 1 < len(shape) else 1
     dp = device_plan(plan, x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         fn = getattr(load(), f"fdx_axis_apply_{_sfx(x)}")
         check(
             fn(dp.handle, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), outer, inner, float(alpha), int(bool(accumulate)), _stream_ptr(x.device)),
@@ -240,7 +258,7 @@ def fused3d(kind: str, plans: Sequence[AxisPlan], xs, outs, alpha: Sequence[floa
     sfx = _sfx(first)
     st = _stream_ptr(dev)
     lib = load()
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         if kind == "laplacian":
             rc = getattr(lib, f"fdx_laplacian3d_{sfx}")(hp, C.c_void_p(xs.data_ptr()), C.c_void_p(outs.data_ptr()), _alphas(alpha), _slab(slab), st)
         elif kind == "divergence":
@@ -275,7 +293,7 @@ def fused3d_ptr(kind: str, plans: Sequence[AxisPlan], in_ptrs: Sequence[int], ou
         ptrs = list(ptrs) + [0] * (3 - len(ptrs))
         return (C.c_void_p * 3)(*[C.c_void_p(int(p)) for p in ptrs])
 
-    with torch.cuda.device(device):
+    with _on_device(device):
         if kind == "laplacian":
             rc = getattr(lib, f"fdx_laplacian3d_{sfx}")(hp, C.c_void_p(int(in_ptrs[0])), C.c_void_p(int(out_ptrs[0])), _alphas(alpha), C.byref(slab), st)
         elif kind == "divergence":

@@ -705,6 +705,10 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       case 6: if constexpr (WZ > 6) phase(IC<6>{}); break;
       case 7: if constexpr (WZ > 7) phase(IC<7>{}); break;
       case 8: if constexpr (WZ > 8) phase(IC<8>{}); break;
+      case 9: if constexpr (WZ > 9) phase(IC<9>{}); break;
+      case 10: if constexpr (WZ > 10) phase(IC<10>{}); break;
+      case 11: if constexpr (WZ > 11) phase(IC<11>{}); break;
+      case 12: if constexpr (WZ > 12) phase(IC<12>{}); break;
       default: break;
     }
     u = (u + 1 == WZ) ? 0 : u + 1;
@@ -852,7 +856,7 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
   case ID:               \
     return launch_cfg<OP, T, P, Cfg<__VA_ARGS__>>(plans, in, out, alpha, sl, st);
 #ifdef FDX_SWEEP
-  if constexpr (OP == LAP && sizeof(T) == 4 && P == 3) {
+  if constexpr (sizeof(T) == 4 && (P == 3 || P == 2)) {
     switch (cfg) {
       FDX_CFG(1, 16, 16, 2, 4, 1)
       FDX_CFG(2, 16, 16, 2, 4, 2)
@@ -876,12 +880,26 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
 #endif
   // defaults from the round-1 sweeps on B200 (tools/sweep_fused.py, profiles/): 64x16-point tiles,
   // 128 threads, 8 TMA stages, 3 CTAs per SM for the light operators
-  constexpr bool heavy = (OP == CURL) || (sizeof(T) == 8 && P >= 3);
-  if constexpr (heavy) {
+  constexpr bool heavy = (OP == CURL) || (sizeof(T) == 8 && P >= 3) || (P >= 5);
+  constexpr bool wide = P >= 5;  // 11/13-tap queues: one row per thread, taller tiles for the halo ratio
+  if constexpr (wide) {
+    switch (cfg) {
+      FDX_CFG(1, 16, 16, 1, 4, 2)
+      default:
+        return launch_cfg<OP, T, P, Cfg<16, 32, 1, 4, 1>>(plans, in, out, alpha, sl, st);
+    }
+  } else if constexpr (heavy) {
     switch (cfg) {
       FDX_CFG(1, 16, 16, 1, 4, 1)
       default:
         return launch_cfg<OP, T, P, Cfg<16, 16, 1, 4, 2>>(plans, in, out, alpha, sl, st);
+    }
+  } else if constexpr (OP == DIV) {
+    // divergence carries one 2P+1 queue for three inputs: 4 rows per thread amortise the per-step cost
+    switch (cfg) {
+      FDX_CFG(1, 16, 8, 2, 8, 3)
+      default:
+        return launch_cfg<OP, T, P, Cfg<16, 8, 4, 4, 2>>(plans, in, out, alpha, sl, st);
     }
   } else {
     switch (cfg) {
@@ -900,7 +918,7 @@ static int fused_radius(const fdx_plan_t plans[3], const T* const in[3], T* cons
   constexpr int V = 16 / sizeof(T);
   if (env_int("FDX_FUSED_DISABLE", 0)) return 0;
   const int P = plans[0]->hi;
-  if (P < 1 || P > 4) return 0;
+  if (P < 1 || P > 6) return 0;
   for (int k = 0; k < 3; ++k) {
     const fdx_plan_s* p = plans[k];
     if (p->lo != -P || p->hi != P) return 0;
@@ -993,6 +1011,12 @@ static int run(const fdx_plan_t plans[3], const T* const in[3], T* const out[3],
       break;
     case 4:
       rc = launch_p<OP, T, 4>(plans, in, out, alpha, sl, st);
+      break;
+    case 5:
+      rc = launch_p<OP, T, 5>(plans, in, out, alpha, sl, st);
+      break;
+    case 6:
+      rc = launch_p<OP, T, 6>(plans, in, out, alpha, sl, st);
       break;
     default:
       break;

@@ -27,6 +27,7 @@ import numpy as np
 import torch
 
 from . import _cabi
+from . import plan as _plan_mod
 from .plan import AxisPlan, axis_plan, axis_plan_t
 from .utils import _check_and_return
 
@@ -89,17 +90,36 @@ def _match_fused(terms: Sequence[Term], n_in: int, n_out: int, spatial):
     return None
 
 
+_fused_memo: dict = {}
+_plan_mod._dependent_caches.append(_fused_memo.clear)
+
+
+def _fused_lookup(terms, n_in: int, n_out: int, spatial):
+    """Memoised recognition of a term list as a fused 3-D operator: (kind, plans, alpha) or None."""
+    key = (terms, n_in, n_out, spatial)
+    hit = _fused_memo.get(key, False)
+    if hit is False:
+        m = _match_fused(terms, n_in, n_out, spatial)
+        if m is None:
+            hit = None
+        else:
+            kind, axis_terms = m
+            hit = (kind, tuple(t.plan(spatial[k]) for k, t in enumerate(axis_terms)), tuple(t.alpha for t in axis_terms))
+        if len(_fused_memo) > 256:
+            _fused_memo.clear()
+        _fused_memo[key] = hit
+    return hit
+
+
 def _execute(terms: Sequence[Term], x: torch.Tensor, n_out: int) -> torch.Tensor:
     """x: (n_in, *spatial) contiguous CUDA tensor -> (n_out, *spatial)."""
     n_in, spatial = x.shape[0], tuple(x.shape[1:])
     out = torch.empty((n_out,) + spatial, dtype=x.dtype, device=x.device)
     if x.numel() == 0:
         return out
-    fused = _match_fused(terms, n_in, n_out, spatial)
+    fused = _fused_lookup(terms, n_in, n_out, spatial)
     if fused is not None:
-        kind, axis_terms = fused
-        plans = [t.plan(spatial[k]) for k, t in enumerate(axis_terms)]
-        alpha = [t.alpha for t in axis_terms]
+        kind, plans, alpha = fused
         xs = x[0] if kind in ("laplacian", "gradient") else [x[0], x[1], x[2]]
         outs = out[0] if kind in ("laplacian", "divergence") else [out[0], out[1], out[2]]
         if _cabi.fused3d(kind, plans, xs, outs, alpha) == 0:
@@ -236,6 +256,8 @@ def _run(x_fields: torch.Tensor, terms, n_out: int) -> torch.Tensor:
     terms = tuple(terms)
     for t in terms:  # validate sizes/methods up front so errors match the reference's ValueError
         t.plan(x_fields.shape[1 + t.axis])
+    if not x_fields.requires_grad or not torch.is_grad_enabled():
+        return _execute(terms, x_fields, n_out)  # skip the autograd.Function round trip
     return _StencilOp.apply(x_fields, terms, n_out)
 
 

@@ -38,6 +38,7 @@ MAX_TAPS = 16  # must match FDX_MAX_TAPS in include/fdx_b200.h
 # Hook used by the parity tests to feed the kernels the reference's own (inexact) coefficients,
 # SURVEY.md section 9 decision 2(i).  None -> exact float64.
 _coeff_override: Optional[Callable] = None
+_dependent_caches: list = []  # clear() callables of caches that hold plans (finite_diff._fused_memo ...)
 
 
 def set_coefficient_source(fn: Optional[Callable]) -> None:
@@ -46,6 +47,8 @@ def set_coefficient_source(fn: Optional[Callable]) -> None:
     _coeff_override = fn
     axis_plan.cache_clear()
     axis_plan_t.cache_clear()
+    for clear in _dependent_caches:
+        clear()
 
 
 def _coeffs(offsets, derivative):

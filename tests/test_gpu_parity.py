@@ -136,6 +136,14 @@ def test_operators_vs_oracle(dtype, method):
     cases = [
         ("laplacian", x3, dict(accuracy=4, step_size=1 / 39)),
         ("laplacian", x3, dict(accuracy=(2, 4, 6), step_size=(0.1, 0.2, 0.3))),
+        ("laplacian", x3, dict(accuracy=8, step_size=1 / 39)),    # radius 5 (BASELINE config 5 stencil)
+        ("laplacian", x3, dict(accuracy=10, step_size=1 / 39)),   # radius 6
+        ("laplacian", x3, dict(accuracy=2, step_size=0.5)),       # radius 2
+        ("laplacian", x3, dict(accuracy=1, step_size=0.5)),       # radius 1
+        ("gradient", x3, dict(accuracy=8, step_size=0.1)),        # radius 4
+        ("divergence", f3, dict(accuracy=10, step_size=0.1)),     # radius 5
+        ("curl", f3, dict(accuracy=8, step_size=0.1)),            # radius 4
+        ("curl", f3, dict(accuracy=1, step_size=0.1)),
         ("laplacian", x2, dict(accuracy=6, step_size=0.3)),
         ("gradient", x3, dict(accuracy=4, step_size=(0.1, 0.2, 0.3))),
         ("gradient", x2, dict(accuracy=(2, 5), step_size=0.5)),
@@ -235,6 +243,35 @@ def test_autograd_dot_product_every_operator(dtype):
         rhs = (gx.double() * x.detach().double()).sum().item()
         norm = (out.detach().double().abs() * g.double().abs()).sum().item()
         assert abs(lhs - rhs) <= tol * norm, (op, kw, lhs, rhs, norm)
+
+
+def test_fused_kernels_cover_forward_and_adjoint():
+    """The 3-D operators and their vjps must run on the fused single-pass kernels (not the composed
+    fallback) for the BASELINE stencils, and agree with the composed axis kernels."""
+    import os
+
+    x = torch.randn(48, 40, 64, device="cuda", requires_grad=True)
+    f = torch.randn(3, 48, 40, 64, device="cuda", requires_grad=True)
+    for acc in (2, 4, 6, 8):
+        for name, arg, kw in (("laplacian", x, {}), ("gradient", x, {}), ("divergence", f, {"keepdims": False}), ("curl", f, {})):
+            if acc == 8 and name == "laplacian":
+                pass
+            out = getattr(fdx, name)(arg, accuracy=acc, step_size=0.1, **kw)
+            assert _cabi.last_kernel().startswith("fused_"), (name, acc, _cabi.last_kernel())
+            g = torch.randn_like(out)
+            (gx,) = torch.autograd.grad(out, arg, g)
+            fused_bwd = _cabi.last_kernel()
+            os.environ["FDX_FUSED_DISABLE"] = "1"
+            try:
+                out2 = getattr(fdx, name)(arg, accuracy=acc, step_size=0.1, **kw)
+                (gx2,) = torch.autograd.grad(out2, arg, g)
+            finally:
+                os.environ["FDX_FUSED_DISABLE"] = "0"
+            tol = 2e-5
+            assert ((out - out2).abs().max() / out2.abs().max()).item() < tol, (name, acc)
+            assert ((gx - gx2).abs().max() / gx2.abs().max()).item() < tol, (name, acc)
+            if acc <= 4:
+                assert fused_bwd.startswith("fused_"), (name, acc, fused_bwd)
 
 
 def test_double_backward_is_the_operator_again():
