@@ -73,6 +73,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 // ------------------------------------------------------------------------------ parameters
 constexpr int kTabMax = 640;   // band coefficients of all 6 sides, carried in the parameter block
 constexpr int kRowsMax = 96;   // band rows of all 6 sides
+constexpr int kMaxPlanes = 383;  // planes one CTA may march through (per-plane flag bytes in shared memory)
 
 template <typename T>
 struct AxisDev {
@@ -93,7 +94,12 @@ struct FusedParams {
   int z_lo, z_hi;      // addressable input planes [z_lo, z_hi]
   int tz_off;          // tensor-map plane index = global plane index + tz_off (= -in_first)
   int chunk, n_chunks, tiles_x, tiles_y;
-  int ablate;  // FDX_SWEEP builds only: skip parts of the work to locate the bottleneck (results are wrong)
+  // fast x bands (band rows fit one 16-byte vector, taps fit three): per-tap coefficient vectors,
+  // xcl[t][v] = tap t of left band row v (column v + t); xcr[t][v] = tap of right band row
+  // v - (V - nr) that sits t columns before the row's own column
+  static constexpr int kXV = 16 / (int)sizeof(T), kXT = 2 * kXV + 1;
+  int xfast, xnt_l, xnt_r;
+  T xcl[kXT][kXV], xcr[kXT][kXV];
   short2 rng[kRowsMax];  // [first, last+1) nonzero band column of every band row
   T tab[kTabMax];
 };
@@ -151,7 +157,7 @@ struct Geometry {
     for (int f = 0; f < Tr::NIN; ++f) b += box_x(f) * box_y(f) * (int)sizeof(T);
     return b;
   }
-  static constexpr int SMEM_BYTES = 512 + CFG::STAGES * STAGE_BYTES;  // barriers + alignment slack
+  static constexpr int SMEM_BYTES = 640 + CFG::STAGES * STAGE_BYTES;  // barriers + plane flags + alignment slack
 };
 
 template <int N>
@@ -200,26 +206,110 @@ __device__ __forceinline__ void add_vec(Vec<double, 2>& acc, const Vec<double, 2
 #pragma unroll
   for (int v = 0; v < 2; ++v) acc.v[v] += x.v[v];
 }
+// dst = c * x + src (three-operand form: the queue shift of the z march)
+__device__ __forceinline__ void fma_to(Vec<float, 4>& dst, float c, const Vec<float, 4>& x, const Vec<float, 4>& src) {
+  const unsigned long long cc = pack2(c, c);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(cc), "l"(pack2(x.v[2 * h], x.v[2 * h + 1])), "l"(pack2(src.v[2 * h], src.v[2 * h + 1])));
+    unpack2(d, dst.v[2 * h], dst.v[2 * h + 1]);
+  }
+}
+__device__ __forceinline__ void fma_to(Vec<double, 2>& dst, double c, const Vec<double, 2>& x, const Vec<double, 2>& src) {
+#pragma unroll
+  for (int v = 0; v < 2; ++v) dst.v[v] = fma(c, x.v[v], src.v[v]);
+}
 
 // ------------------------------------------------------------------------------ the kernel
+// Shared-memory accesses of the hot path use 32-bit shared-window addresses (no generic->shared
+// conversion inside the loop); `volatile` keeps them behind the mbarrier wait.
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> lds_vec(uint32_t addr) {
+  Vec<T, V> r;
+  if constexpr (sizeof(T) == 4) {
+    static_assert(V == 4, "fp32 vectors are 4 wide");
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(addr));
+  } else {
+    static_assert(V == 2, "fp64 vectors are 2 wide");
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(addr));
+  }
+  return r;
+}
+template <typename T, int V>
+__device__ __forceinline__ void stg_vec(uint64_t addr, const Vec<T, V>& r) {
+  if constexpr (sizeof(T) == 4)
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
+  else
+    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(addr), "d"(r.v[0]), "d"(r.v[1]) : "memory");
+}
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// Which field feeds the q-th y-derivative / x-derivative of the in-plane part
+//   LAP : ya0 = D1 x       xa0 = D2 x
+//   DIV : ya0 = D1 x1      xa0 = D2 x2
+//   GRAD: ya0 = D1 x       xa0 = D2 x
+//   CURL: ya0 = D1 x2, ya1 = D1 x0      xa0 = D2 x1, xa1 = D2 x0
+template <Op OP>
+struct InPlane {
+  static constexpr int NY = OP == CURL ? 2 : 1, NX = OP == CURL ? 2 : 1;
+  __host__ __device__ static constexpr int yfield(int q) { return OP == DIV ? 1 : (OP == CURL ? (q == 0 ? 2 : 0) : 0); }
+  __host__ __device__ static constexpr int xfield(int q) { return OP == DIV ? 2 : (OP == CURL ? (q == 0 ? 1 : 0) : 0); }
+};
+
 template <Op OP, typename T, int P, typename CFG>
 __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     fused3d_kernel(const __grid_constant__ FusedParams<T> prm) {
   using G = Geometry<OP, T, P, CFG>;
   using Tr = OpTraits<OP>;
+  using IP = InPlane<OP>;
   constexpr int V = G::V, RY = CFG::RY, WZ = G::WZ, STAGES = CFG::STAGES, HX = G::HX, HXV = G::HXV;
+  constexpr int NY = IP::NY, NX = IP::NX;
   constexpr int TRW = 32 / CFG::TXV;  // thread rows per warp
   constexpr int WR = TRW * RY;        // grid rows per warp
+  // planes in flight: the stage refilled at step `it` was released at step it - (STAGES - LOOK), so
+  // with LOOK = STAGES - 2 the issuing thread almost never waits for the slowest warp
+  constexpr int LOOK = STAGES >= 4 ? STAGES - 2 : STAGES - 1;
   static_assert(CFG::TXV == 16 || CFG::TXV == 32, "a warp must cover whole tile rows");
+  static_assert(STAGES * 16 <= 128, "barrier area");
   using VT = Vec<T, V>;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // barriers first, then the stage ring rounded up to 128 B for TMA; offsets (not re-derived
-  // pointers) so the compiler keeps the shared address space and emits LDS
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* empty_bar = full_bar + STAGES;
-  const uint32_t raw_u32 = smem_u32(smem_raw);
-  const uint32_t ring_off = ((raw_u32 + 256u + 127u) & ~127u) - raw_u32;
+  // barriers first (full[STAGES], empty[STAGES]), one flag byte per plane of the march at +128, then
+  // the stage ring rounded up to 128 B for TMA
+  uint32_t smem0 = smem_u32(smem_raw);
+  asm volatile("" : "+r"(smem0));  // opaque: computed once, kept in a register
+  const uint32_t ring = (smem0 + 512u + 127u) & ~127u;
+  const uint32_t bar_full = smem0, bar_empty = smem0 + 8u * STAGES, flag_base = smem0 + 128u;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -243,27 +333,42 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], G::NT / 32);
+      mbar_init_a(bar_full + 8u * s, 1);
+      mbar_init_a(bar_empty + 8u * s, G::NT / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- CTA classes (uniform): only `edge` CTAs and z-boundary planes ever enter the cold section
+  const bool xedge_l = (tile_x == 0) && prm.ax[2].nl > 0;  // first / last tile along x hold the whole
+  const bool xedge_r = (tile_x == prm.tiles_x - 1) && prm.ax[2].nr > 0;  // left / right band (host-checked)
+  const bool yedge = (y0 < prm.ax[1].nl) || (y0 + G::TY > n1 - prm.ax[1].nr);
+  const bool edge = xedge_l || xedge_r || yedge;
+  // per-plane flags of this CTA's march, one byte each: the loop reads them instead of re-deriving them
+  enum : uint32_t { F_INR = 1, F_EMIT = 2, F_ZB = 4, F_SLOW = 8 };
+  for (int i = tid; i < n_planes; i += G::NT) {
+    const int z = zin0 + i, zo = z - P;
+    const bool inr = z >= zs && z < ze;                                             // an output plane of ours
+    const bool zb = inr && (z < prm.ax[0].nl || z >= n0 - prm.ax[0].nr);            // next to a physical z boundary
+    const bool emit = zo >= zs && !(zo < prm.ax[0].nl || zo >= n0 - prm.ax[0].nr);  // plane z - P leaves the queue
+    const uint32_t f = (inr ? F_INR : 0u) | (emit ? F_EMIT : 0u) | (zb ? F_ZB : 0u) | ((inr && (edge || zb)) ? F_SLOW : 0u);
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(flag_base + (uint32_t)i), "r"(f) : "memory");
   }
   __syncthreads();
 
   // TMA issue (thread 0 only): plane `it` of this CTA's march goes to stage it % STAGES
   auto issue = [&](int it) {
     const int s = it % STAGES;
-    if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);  // all warps released it
-    mbar_expect_tx(&full_bar[s], G::tx_bytes());
-    unsigned char* dst = smem_raw + ring_off + (size_t)s * G::STAGE_BYTES;
-    const int zc = zin0 + it + prm.tz_off;
+    if (it >= STAGES) mbar_wait_a(bar_empty + 8u * s, ((it / STAGES) - 1) & 1);  // all warps released it
+    mbar_expect_tx_a(bar_full + 8u * s, G::tx_bytes());
+    const uint32_t dst = ring + (uint32_t)s * G::STAGE_BYTES;
+    const int zt = zin0 + it + prm.tz_off;
 #pragma unroll
     for (int f = 0; f < Tr::NIN; ++f)
-      tma_load_3d(dst + G::field_off(f), &prm.tmap[f], &full_bar[s], x0 - G::xoff(f), y0 - G::yoff(f), zc);
+      tma_load_3d_a(dst + G::field_off(f), &prm.tmap[f], bar_full + 8u * s, x0 - G::xoff(f), y0 - G::yoff(f), zt);
   };
   if (tid == 0) {
     for (int f = 0; f < Tr::NIN; ++f) asm volatile("prefetch.tensormap [%0];" ::"l"(&prm.tmap[f]) : "memory");
-    for (int it = 0; it < STAGES - 1 && it < n_planes; ++it) issue(it);
+    for (int it = 0; it < LOOK && it < n_planes; ++it) issue(it);
   }
 
   const int tx = tid % CFG::TXV, ty = tid / CFG::TXV;
@@ -272,38 +377,34 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   const AxisDev<T>& A0 = prm.ax[0];
   const AxisDev<T>& A1 = prm.ax[1];
   const AxisDev<T>& A2 = prm.ax[2];
-  const int64_t plane = (int64_t)n1 * n2;
+  const int plane = n1 * n2;  // < 2^31, host-checked
   // n2 % V == 0, so a vector is entirely in or out of the grid
-  bool rok[RY];
+  // row j of this thread lies inside the grid: bit j (opaque, so that it stays one register)
+  uint32_t rmask = 0;
 #pragma unroll
-  for (int j = 0; j < RY; ++j) rok[j] = (xg < n2) && (yg + j < n1);
-#ifdef FDX_ABLATION
-  const bool no_bands = prm.ablate & 32;
-#define ABL(bit) (prm.ablate & (bit))
-#else
-  constexpr bool no_bands = false;
-#define ABL(bit) false
-#endif
-  const bool yband = !no_bands && !(ABL(128)) && rok[0] && ((yg < A1.nl) || (yg + RY > n1 - A1.nr));
-  // CTA-uniform: first / last tile along x (they hold the whole left / right band, host-checked)
-  const bool xedge_l = !no_bands && !(ABL(64)) && (tile_x == 0) && A2.nl > 0;
-  const bool xedge_r = !no_bands && !(ABL(64)) && (tile_x == prm.tiles_x - 1) && A2.nr > 0;
+  for (int j = 0; j < RY; ++j) rmask |= ((xg < n2) && (yg + j < n1)) ? (1u << j) : 0u;
+  asm volatile("" : "+r"(rmask));
+  auto rok = [&](int j) { return (rmask >> j) & 1u; };
+
+  const bool yband = yedge && rok(0) && ((yg < A1.nl) || (yg + RY > n1 - A1.nr));
+
   const int64_t thread_ofs = (int64_t)yg * n2 + xg;  // this thread's first element inside a plane
-  // byte offset (from smem_raw, stage 0) of this thread's vector in tile row ty*RY of each field
-  uint32_t toffb[Tr::NIN];
+  // shared address (stage 0) of this thread's vector in tile row ty*RY of each field
+  uint32_t tb[Tr::NIN];
 #pragma unroll
   for (int f = 0; f < Tr::NIN; ++f)
-    toffb[f] = ring_off + G::field_off(f) + (uint32_t)sizeof(T) * ((ty * RY) * G::box_x(f) + G::xoff(f) + tx * V);
-
-  VT acc[Tr::NACC][WZ][RY];
+    tb[f] = ring + G::field_off(f) + (uint32_t)sizeof(T) * ((ty * RY) * G::box_x(f) + G::xoff(f) + tx * V);
+  // output row bases: address of element (plane 0, row yg + j, column xg) of every output, held in
+  // registers (opaque) so that a store costs one IMAD.WIDE for its address
+  uint64_t ob[Tr::NOUT][RY];
 #pragma unroll
-  for (int a = 0; a < Tr::NACC; ++a)
+  for (int o = 0; o < Tr::NOUT; ++o)
 #pragma unroll
-    for (int s = 0; s < WZ; ++s)
-#pragma unroll
-      for (int j = 0; j < RY; ++j)
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc[a][s][j].v[v] = 0;
+    for (int j = 0; j < RY; ++j) {
+      ob[o][j] = (uint64_t)(uintptr_t)(prm.out[o] + thread_ofs + (int64_t)j * n2);
+      asm volatile("" : "+l"(ob[o][j]));
+    }
+  const int plane_b = plane * (int)sizeof(T);  // < 2^31, host-checked
 
   // ------------------------------------------------------------------ hot in-plane helpers
   // D_y, streaming: centre row i of the RY+2P rows a thread sees feeds output rows j = i-2P .. i
@@ -318,17 +419,17 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
         fma_vec<false>(ys[j], A1.c[k], ci);
     }
   };
-  // D_x for one row: `rowp` points at this thread's vector inside a tile row that has x halos
-  auto dx_main = [&](const T* rowp, const VT& centre) {
+  // D_x for one row: `row` is the shared address of this thread's vector inside a tile row with x halos
+  auto dx_main = [&](uint32_t row, const VT& centre) {
     T w[(2 * HXV + 1) * V];
 #pragma unroll
-    for (int u = 0; u < HXV; ++u) {
-      const VT l = *reinterpret_cast<const VT*>(rowp - (HXV - u) * V);
-      const VT rr = *reinterpret_cast<const VT*>(rowp + (u + 1) * V);
+    for (int h = 0; h < HXV; ++h) {
+      const VT l = lds_vec<T, V>(row - (uint32_t)((HXV - h) * V * sizeof(T)));
+      const VT rr = lds_vec<T, V>(row + (uint32_t)((h + 1) * V * sizeof(T)));
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        w[u * V + v] = l.v[v];
-        w[(HXV + 1 + u) * V + v] = rr.v[v];
+        w[h * V + v] = l.v[v];
+        w[(HXV + 1 + h) * V + v] = rr.v[v];
       }
     }
 #pragma unroll
@@ -355,8 +456,6 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     c0 = rg.x, c1 = rg.y;
     colbase = left ? 0 : A.n - A.wr;
   };
-  // y band of global row y: taps from the tile when it holds all of them, else from global memory.
-  // tcol: smem address of (tile row 0, this thread's x); gcol: global address of (z, row 0, xg)
   // taps c in [c0, c1) in batches of four: all loads of a batch are issued before the first FMA, so
   // a cold path costs about one load latency per batch instead of one per tap
   auto band_dot_vec = [&](int tab, int c0, int c1, auto load /* (int c) -> VT */) {
@@ -380,6 +479,8 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     }
     return a;
   };
+  // y band of global row y: taps from the tile when it holds all of them, else from global memory.
+  // tcol: generic address of (tile row 0, this thread's x); gcol: global address of (z, row 0, xg)
   auto band_y = [&](const T* tcol, int pitch, int boxy, const T* gcol, int y) {
     int tab, c0, c1, cb;
     band_rng(A1, y, tab, c0, c1, cb);
@@ -460,6 +561,58 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       }
     }
   };
+  // x bands, fast form (prm.xfast): every band row of a side lies in ONE thread's vector and its taps
+  // in three vectors, so the edge thread evaluates them from registers with static indices; the
+  // taps run in ascending column order like the reference's sum
+  const bool xfast = prm.xfast != 0;
+  const bool xmine_l = xedge_l && tx == 0, xmine_r = xedge_r && xg == n2 - V;
+  auto xband_fast = [&](uint32_t row /* shared address of this thread's vector in the row */, VT (&x)) {
+    constexpr int XT = FusedParams<T>::kXT;
+    if (xmine_l) {
+      T w[3 * V];
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        const VT t = lds_vec<T, V>(row + (uint32_t)(h * V * sizeof(T)));
+#pragma unroll
+        for (int v = 0; v < V; ++v) w[h * V + v] = t.v[v];
+      }
+      T a[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) a[v] = 0;
+#pragma unroll
+      for (int t = 0; t < XT; ++t) {
+        if (t < prm.xnt_l) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) a[v] = fma(prm.xcl[t][v], w[v + t], a[v]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (v < A2.nl) x.v[v] = a[v] * A2.alpha;
+    }
+    if (xmine_r) {
+      T w[3 * V];
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        const VT t = lds_vec<T, V>(row - (uint32_t)((2 - h) * V * sizeof(T)));
+#pragma unroll
+        for (int v = 0; v < V; ++v) w[h * V + v] = t.v[v];
+      }
+      T a[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) a[v] = 0;
+#pragma unroll
+      for (int t = XT - 1; t >= 0; --t) {
+        if (t < prm.xnt_r) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) a[v] = fma(prm.xcr[t][v], w[2 * V + v - t], a[v]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (v >= V - A2.nr) x.v[v] = a[v] * A2.alpha;
+    }
+  };
   // z band of plane z (always from global memory: the other planes are not in the ring)
   auto band_z = [&](const T* gcol0 /* global address of (plane 0, this row, xg) */, int z) {
     int tab, c0, c1, cb;
@@ -470,248 +623,216 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     for (int v = 0; v < V; ++v) a.v[v] *= A0.alpha;
     return a;
   };
-  auto zband = [&](int z) { return !no_bands && !(ABL(256)) && (z < A0.nl || z >= n0 - A0.nr); };
-  auto is_yband = [&](int j) { return rok[j] && (yg + j < A1.nl || yg + j >= n1 - A1.nr); };
+  auto is_yband = [&](int j) { return rok(j) && (yg + j < A1.nl || yg + j >= n1 - A1.nr); };
   auto store = [&](int o, int z, int j, const VT& val) {
-#ifdef FDX_ABLATION
-    if (prm.ablate & 8) return;
-#endif
-    if (rok[j]) st_vec<T, V>(prm.out[o] + (int64_t)z * plane + thread_ofs + (int64_t)j * n2, val);
+    if (rok(j)) stg_vec<T, V>(ob[o][j] + (uint64_t)((int64_t)z * (int64_t)plane_b), val);
   };
 
   // ---- march along z ---------------------------------------------------------------------
-  int u = 0;                // it % WZ   (phase of the register queue)
-  int stage = 0;            // it % STAGES
-  uint32_t stage_off = 0;   // stage * STAGE_BYTES
+  // The register queue is a shift register: before plane zc arrives, q[a][i][j] holds the partial sum
+  // of output plane zc + P - 1 - i, which has received its taps 0 .. i.  Plane zc completes the oldest
+  // entry (tap 2P, emitted) and moves every other entry one place with a three-operand FMA,
+  //     q[i] = q[i-1] + c_i * x      (i = 2P-1 .. 1),      q[0] = c_0 * x,
+  // so the rotation costs nothing, all register indices are static and there is one copy of the code.
+  VT q[Tr::NACC][2 * P][RY];
+#pragma unroll
+  for (int a = 0; a < Tr::NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 2 * P; ++i)
+#pragma unroll
+      for (int j = 0; j < RY; ++j)
+#pragma unroll
+        for (int v = 0; v < V; ++v) q[a][i][j].v[v] = 0;
+
+  int stage = 0;           // it % STAGES
+  uint32_t soff = 0;       // stage * STAGE_BYTES
   uint32_t full_parity = 0;
   int zc = zin0;
+  auto lds_flag = [&](int i) {
+    uint32_t f;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(f) : "r"(flag_base + (uint32_t)i));
+    return f;
+  };
+  uint32_t fl_next = lds_flag(0);
   for (int it = 0; it < n_planes; ++it, ++zc) {
-    const bool inr = (unsigned)(zc - zs) < (unsigned)(ze - zs);  // this plane is also an output plane of ours
-    const bool zb = inr && zband(zc);
-    // keep STAGES-1 planes in flight: the stage consumed at step it-1 is refilled now
-    if (tid == 0 && it + STAGES - 1 < n_planes) issue(it + STAGES - 1);
-    mbar_wait(&full_bar[stage], full_parity);
-    auto tile = [&](int f) { return reinterpret_cast<const T*>(smem_raw + ring_off + stage_off + G::field_off(f)); };
-    // address of this thread's vector in tile row (ty*RY + i) of field f
-    auto tptr = [&](int f, int i) {
-      return reinterpret_cast<const T*>(smem_raw + stage_off + toffb[f]) + i * G::box_x(f);
-    };
-    const int64_t zofs = (int64_t)zc * plane;
+    const uint32_t fl = fl_next;
+    const bool inr = fl & F_INR;    // this plane is also an output plane of ours
+    const bool zb = fl & F_ZB;      // ... next to a physical z boundary
+    const bool slow = fl & F_SLOW;  // the in-plane result needs the cold section
+    const bool emit = fl & F_EMIT;  // output plane zc - P is complete after this step
+    if (tid == 0 && it + LOOK < n_planes) issue(it + LOOK);
+    mbar_wait_a(bar_full + 8u * stage, full_parity);
+    fl_next = lds_flag(it + 1);  // (one byte past the last plane is still inside the flag area)
 
-    VT zv[Tr::NACC][RY];   // values scattered along z
-    VT tin[Tr::NACC][RY];  // in-plane contribution to plane zc of each accumulator set
-    // ---------------- in-plane part (one copy of this code: it does not depend on the queue phase)
-    if constexpr (OP == LAP || OP == GRAD) {
-      VT ys[RY], xs[RY];
+    VT zv[Tr::NACC][RY];   // values that enter the z taps
+    VT tin[Tr::NACC][RY];  // in-plane contribution to output plane zc of each accumulator set
+    if (inr) {
+      VT ya[NY][RY], xa[NX][RY];  // raw in-plane derivatives of plane zc
+      // ---------------- hot: loads and in-plane taps
+      if constexpr (OP == LAP || OP == GRAD) {
 #pragma unroll
-      for (int i = 0; i < RY + 2 * P; ++i) {
-#ifdef FDX_ABLATION
-        VT ci;
-        if (prm.ablate & 16) {
+        for (int i = 0; i < RY + 2 * P; ++i) {
+          const uint32_t row = tb[0] + soff + (uint32_t)(i * G::box_x(0) * sizeof(T));
+          const VT ci = lds_vec<T, V>(row);
+          dy_feed(ya[0], ci, i);
+          if (i >= P && i < P + RY) {
+            zv[0][i - P] = ci;
+            xa[0][i - P] = dx_main(row, ci);
+          }
+        }
+      } else if constexpr (OP == DIV) {
 #pragma unroll
-          for (int v = 0; v < V; ++v) ci.v[v] = (T)1;
-        } else {
-          ci = *reinterpret_cast<const VT*>(tptr(0, i));
-        }
-        if (inr && !(prm.ablate & 2)) dy_feed(ys, ci, i);
-        if (i >= P && i < P + RY) {
-          zv[0][i - P] = ci;
-          if (inr && !(prm.ablate & 1)) xs[i - P] = dx_main(tptr(0, i), ci);
-        }
-#else
-        const VT ci = *reinterpret_cast<const VT*>(tptr(0, i));
-        if (inr) dy_feed(ys, ci, i);
-        if (i >= P && i < P + RY) {
-          zv[0][i - P] = ci;
-          if (inr) xs[i - P] = dx_main(tptr(0, i), ci);
-        }
-#endif
-      }
-      if (inr) {
-        if (yband) {
+        for (int j = 0; j < RY; ++j) zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)(j * G::box_x(0) * sizeof(T)));
 #pragma unroll
-          for (int j = 0; j < RY; ++j)
-            if (is_yband(j)) ys[j] = band_y(tile(0) + HX + tx * V, G::box_x(0), G::box_y(0), prm.in[0] + zofs + xg, yg + j);
-        }
-        if (xedge_l || xedge_r) xband_fix(tile(0), G::box_x(0), P, xs);
+        for (int i = 0; i < RY + 2 * P; ++i)
+          dy_feed(ya[0], lds_vec<T, V>(tb[1] + soff + (uint32_t)(i * G::box_x(1) * sizeof(T))), i);
 #pragma unroll
         for (int j = 0; j < RY; ++j) {
-          if constexpr (OP == LAP) {
-            tin[0][j] = ys[j];
-            add_vec(tin[0][j], xs[j]);
-          } else {
-            store(1, zc, j, ys[j]);
-            store(2, zc, j, xs[j]);
+          const uint32_t row = tb[2] + soff + (uint32_t)(j * G::box_x(2) * sizeof(T));
+          xa[0][j] = dx_main(row, lds_vec<T, V>(row));
+        }
+      } else {  // CURL
+#pragma unroll
+        for (int i = 0; i < RY + 2 * P; ++i) {
+          const VT ci = lds_vec<T, V>(tb[2] + soff + (uint32_t)(i * G::box_x(2) * sizeof(T)));
+          dy_feed(ya[0], ci, i);                        // D1 x2
+          if (i >= P && i < P + RY) zv[0][i - P] = ci;  // x2 -> -D0 x2 into out_1
+        }
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          const uint32_t row = tb[1] + soff + (uint32_t)(j * G::box_x(1) * sizeof(T));
+          zv[1][j] = lds_vec<T, V>(row);      // x1 -> +D0 x1 into out_2
+          xa[0][j] = dx_main(row, zv[1][j]);  // D2 x1
+        }
+#pragma unroll
+        for (int i = 0; i < RY + 2 * P; ++i) {
+          const uint32_t row = tb[0] + soff + (uint32_t)(i * G::box_x(0) * sizeof(T));
+          const VT ci = lds_vec<T, V>(row);
+          dy_feed(ya[1], ci, i);                                       // D1 x0
+          if (i >= P && i < P + RY) xa[1][i - P] = dx_main(row, ci);  // D2 x0
+        }
+      }
+      // ---------------- cold: rows / columns next to a physical boundary of the grid
+      if (slow && edge) {
+        const int64_t zofs = (int64_t)zc * plane;
+        auto tile = [&](int f) { return reinterpret_cast<const T*>(smem_raw + (ring - smem0) + soff + G::field_off(f)); };
+        if (yband) {
+#pragma unroll
+          for (int qq = 0; qq < NY; ++qq) {
+            const int f = IP::yfield(qq);
+#pragma unroll
+            for (int j = 0; j < RY; ++j)
+              if (is_yband(j))
+                ya[qq][j] = band_y(tile(f) + G::xoff(f) + tx * V, G::box_x(f), G::box_y(f), prm.in[f] + zofs + xg, yg + j);
+          }
+        }
+        if (xedge_l || xedge_r) {
+#pragma unroll
+          for (int qq = 0; qq < NX; ++qq) {
+            const int f = IP::xfield(qq);
+            if (xfast) {
+              if (xmine_l || xmine_r) {
+#pragma unroll
+                for (int j = 0; j < RY; ++j)
+                  xband_fast(tb[f] + soff + (uint32_t)((G::yoff(f) + j) * G::box_x(f) * sizeof(T)), xa[qq][j]);
+              }
+            } else {
+              xband_fix(tile(f), G::box_x(f), G::yoff(f), xa[qq]);
+            }
           }
         }
       }
-    } else if constexpr (OP == DIV) {
+      // ---------------- in-plane results: straight out, or towards output plane zc of the queue
 #pragma unroll
-      for (int j = 0; j < RY; ++j) zv[0][j] = *reinterpret_cast<const VT*>(tptr(0, j));
-      if (inr) {
-        VT ys[RY], xs[RY];
-#pragma unroll
-        for (int i = 0; i < RY + 2 * P; ++i) dy_feed(ys, *reinterpret_cast<const VT*>(tptr(1, i)), i);
-#pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          const VT ctr = *reinterpret_cast<const VT*>(tptr(2, j));
-          xs[j] = dx_main(tptr(2, j), ctr);
-        }
-        if (yband) {
-#pragma unroll
-          for (int j = 0; j < RY; ++j)
-            if (is_yband(j)) ys[j] = band_y(tile(1) + tx * V, G::box_x(1), G::box_y(1), prm.in[1] + zofs + xg, yg + j);
-        }
-        if (xedge_l || xedge_r) xband_fix(tile(2), G::box_x(2), 0, xs);
-#pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          tin[0][j] = ys[j];
-          add_vec(tin[0][j], xs[j]);
-        }
-      }
-    } else {  // CURL
-      // out_0 = D1 x2 - D2 x1 ; out_1 = D2 x0 - D0 x2 (acc set 0) ; out_2 = D0 x1 - D1 x0 (acc set 1)
-      VT y2[RY], x1[RY], y0v[RY], x0v[RY];
-#pragma unroll
-      for (int i = 0; i < RY + 2 * P; ++i) {
-        const VT ci = *reinterpret_cast<const VT*>(tptr(2, i));
-        if (inr) dy_feed(y2, ci, i);                  // D1 x2
-        if (i >= P && i < P + RY) zv[0][i - P] = ci;  // x2 -> -D0 x2 into out_1
-      }
-#pragma unroll
-      for (int j = 0; j < RY; ++j) zv[1][j] = *reinterpret_cast<const VT*>(tptr(1, j));  // x1 -> +D0 x1 into out_2
-      if (inr) {
-#pragma unroll
-        for (int i = 0; i < RY + 2 * P; ++i) {
-          const VT ci = *reinterpret_cast<const VT*>(tptr(0, i));
-          dy_feed(y0v, ci, i);                                              // D1 x0
-          if (i >= P && i < P + RY) x0v[i - P] = dx_main(tptr(0, i), ci);  // D2 x0
-        }
-#pragma unroll
-        for (int j = 0; j < RY; ++j) x1[j] = dx_main(tptr(1, j), zv[1][j]);  // D2 x1
-        if (yband) {
-#pragma unroll
-          for (int j = 0; j < RY; ++j)
-            if (is_yband(j)) {
-              y2[j] = band_y(tile(2) + tx * V, G::box_x(2), G::box_y(2), prm.in[2] + zofs + xg, yg + j);
-              y0v[j] = band_y(tile(0) + HX + tx * V, G::box_x(0), G::box_y(0), prm.in[0] + zofs + xg, yg + j);
-            }
-        }
-        if (xedge_l || xedge_r) {
-          xband_fix(tile(1), G::box_x(1), 0, x1);
-          xband_fix(tile(0), G::box_x(0), P, x0v);
-        }
-#pragma unroll
-        for (int j = 0; j < RY; ++j) {
+      for (int j = 0; j < RY; ++j) {
+        if constexpr (OP == LAP || OP == DIV) {
+          tin[0][j] = ya[0][j];
+          add_vec(tin[0][j], xa[0][j]);
+        } else if constexpr (OP == GRAD) {
+          store(1, zc, j, ya[0][j]);
+          store(2, zc, j, xa[0][j]);
+        } else {
           VT o0;
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            o0.v[v] = y2[j].v[v] - x1[j].v[v];
-            tin[0][j].v[v] = x0v[j].v[v];
-            tin[1][j].v[v] = -y0v[j].v[v];
+            o0.v[v] = ya[0][j].v[v] - xa[0][j].v[v];
+            tin[0][j].v[v] = xa[1][j].v[v];
+            tin[1][j].v[v] = -ya[1][j].v[v];
           }
           store(0, zc, j, o0);
+        }
+      }
+      if (zb) {  // cold: plane next to a physical z boundary, one-sided taps gathered directly
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          if (!rok(j)) continue;
+          const int64_t cofs = thread_ofs + (int64_t)j * n2;
+          if constexpr (OP == LAP || OP == DIV || OP == GRAD) {
+            VT zz = band_z(prm.in[0] + cofs, zc);
+            if constexpr (OP != GRAD) add_vec(zz, tin[0][j]);
+            store(0, zc, j, zz);
+          } else {
+            const VT z2 = band_z(prm.in[2] + cofs, zc), z1 = band_z(prm.in[1] + cofs, zc);
+            VT o1, o2;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              o1.v[v] = tin[0][j].v[v] - z2.v[v];
+              o2.v[v] = tin[1][j].v[v] + z1.v[v];
+            }
+            store(1, zc, j, o1);
+            store(2, zc, j, o2);
+          }
+        }
+      }
+    } else {  // warm-up / cool-down plane: only the z taps are wanted
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        if constexpr (OP == LAP || OP == GRAD) {
+          zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)((P + j) * G::box_x(0) * sizeof(T)));
+        } else if constexpr (OP == DIV) {
+          zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)(j * G::box_x(0) * sizeof(T)));
+        } else {
+          zv[0][j] = lds_vec<T, V>(tb[2] + soff + (uint32_t)((P + j) * G::box_x(2) * sizeof(T)));
+          zv[1][j] = lds_vec<T, V>(tb[1] + soff + (uint32_t)(j * G::box_x(1) * sizeof(T)));
         }
       }
     }
     // this warp no longer reads the stage: release it (one arrive per warp)
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (lane == 0) mbar_arrive_a(bar_empty + 8u * stage);
     if (++stage == STAGES) {
-      stage = 0, stage_off = 0, full_parity ^= 1u;
+      stage = 0, soff = 0, full_parity ^= 1u;
     } else {
-      stage_off += G::STAGE_BYTES;
+      soff += G::STAGE_BYTES;
     }
 
-    // ---------------- planes next to a physical z boundary: one-sided taps, gathered directly
-    if (zb) {
+    // ---------------- z taps: complete the oldest queue entry, shift the others
 #pragma unroll
-      for (int j = 0; j < RY; ++j) {
-        if (!rok[j]) continue;
-        const int64_t cofs = thread_ofs + (int64_t)j * n2;
-        if constexpr (OP == LAP || OP == DIV || OP == GRAD) {
-          VT zz = band_z(prm.in[0] + cofs, zc);
-          if constexpr (OP != GRAD) add_vec(zz, tin[0][j]);
-          store(0, zc, j, zz);
-        } else {
-          const VT z2 = band_z(prm.in[2] + cofs, zc), z1 = band_z(prm.in[1] + cofs, zc);
-          VT o1, o2;
+    for (int a = 0; a < Tr::NACC; ++a) {
+      const T sgn = (OP == CURL && a == 0) ? (T)-1 : (T)1;
+      if (emit) {  // output plane zc - P
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            o1.v[v] = tin[0][j].v[v] - z2.v[v];
-            o2.v[v] = tin[1][j].v[v] + z1.v[v];
-          }
-          store(1, zc, j, o1);
-          store(2, zc, j, o2);
+        for (int j = 0; j < RY; ++j) {
+          VT o;
+          fma_to(o, sgn * A0.c[2 * P], zv[a][j], q[a][2 * P - 1][j]);
+          store(OP == CURL ? a + 1 : 0, zc - P, j, o);
         }
       }
+#pragma unroll
+      for (int i = 2 * P - 1; i >= 1; --i)
+#pragma unroll
+        for (int j = 0; j < RY; ++j) fma_to(q[a][i][j], sgn * A0.c[i], zv[a][j], q[a][i - 1][j]);
+#pragma unroll
+      for (int j = 0; j < RY; ++j) fma_vec<true>(q[a][0][j], sgn * A0.c[0], zv[a][j]);
     }
-    const bool add_tin = inr && !zb && (OP != GRAD);
-    const int zo = zc - P;
-    const bool emit = (zo >= zs) && (zo < ze) && !zband(zo);
-
-    // ---------------- scatter along z into the register queue (WZ copies, one per queue phase):
-    // plane zc feeds output z' = zc + P - k with tap k; slot(z') = (it - k) mod WZ
-    auto phase = [&](auto U_) {
-      constexpr int U = decltype(U_)::value;
-#ifdef FDX_ABLATION
-      if (prm.ablate & 4) {
-        if (emit) store(0, zo, 0, zv[0][0]);
-        return;
-      }
-#endif
-#pragma unroll
-      for (int a = 0; a < Tr::NACC; ++a) {
-#pragma unroll
-        for (int k = 0; k < WZ; ++k) {
-          const int slot = ((U - k) % WZ + WZ) % WZ;
-          const T cz = (OP == CURL && a == 0) ? -A0.c[k] : A0.c[k];
-#pragma unroll
-          for (int j = 0; j < RY; ++j) {
-            if (k == 0)
-              fma_vec<true>(acc[a][slot][j], cz, zv[a][j]);
-            else
-              fma_vec<false>(acc[a][slot][j], cz, zv[a][j]);
-          }
-        }
-      }
-      if (add_tin) {  // in-plane part of plane zc goes to the slot of z' = zc (tap k = P)
-        const int slot_c = ((U - P) % WZ + WZ) % WZ;
+    if constexpr (OP != GRAD) {
+      if (inr && !zb) {  // in-plane part of plane zc joins its output (which has just received tap P)
 #pragma unroll
         for (int a = 0; a < Tr::NACC; ++a)
 #pragma unroll
-          for (int j = 0; j < RY; ++j) add_vec(acc[a][slot_c][j], tin[a][j]);
+          for (int j = 0; j < RY; ++j) add_vec(q[a][P][j], tin[a][j]);
       }
-      if (emit) {  // the output plane zc - P is complete
-        const int slot_o = ((U - 2 * P) % WZ + WZ) % WZ;
-#pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          if constexpr (OP == LAP || OP == DIV || OP == GRAD) {
-            store(0, zo, j, acc[0][slot_o][j]);
-          } else {
-            store(1, zo, j, acc[0][slot_o][j]);
-            store(2, zo, j, acc[1][slot_o][j]);
-          }
-        }
-      }
-    };
-    switch (u) {
-      case 0: phase(IC<0>{}); break;
-      case 1: phase(IC<1>{}); break;
-      case 2: phase(IC<2>{}); break;
-      case 3: if constexpr (WZ > 3) phase(IC<3>{}); break;
-      case 4: if constexpr (WZ > 4) phase(IC<4>{}); break;
-      case 5: if constexpr (WZ > 5) phase(IC<5>{}); break;
-      case 6: if constexpr (WZ > 6) phase(IC<6>{}); break;
-      case 7: if constexpr (WZ > 7) phase(IC<7>{}); break;
-      case 8: if constexpr (WZ > 8) phase(IC<8>{}); break;
-      case 9: if constexpr (WZ > 9) phase(IC<9>{}); break;
-      case 10: if constexpr (WZ > 10) phase(IC<10>{}); break;
-      case 11: if constexpr (WZ > 11) phase(IC<11>{}); break;
-      case 12: if constexpr (WZ > 12) phase(IC<12>{}); break;
-      default: break;
     }
-    u = (u + 1 == WZ) ? 0 : u + 1;
   }
 }
 
@@ -804,8 +925,37 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
       rows_used += rows;
     }
   }
+  {
+    // fast x bands: rows in one vector, row r's taps inside columns [r, r + nt)
+    constexpr int XV = FusedParams<T>::kXV, XT = FusedParams<T>::kXT;
+    const fdx_plan_s* px = plans[2];
+    const int ntl = px->wl - px->nl + 1, ntr = px->wr - px->nr + 1;
+    bool ok = px->nl <= XV && px->nr <= XV && ntl >= 1 && ntr >= 1 && ntl <= XT && ntr <= XT && n2 >= 3 * XV;
+    for (int t = 0; t < XT; ++t)
+      for (int v = 0; v < XV; ++v) prm.xcl[t][v] = prm.xcr[t][v] = (T)0;
+    for (int r = 0; ok && r < px->nl; ++r)
+      for (int c = 0; c < px->wl; ++c) {
+        const double h = px->h_band_l[r * px->wl + c];
+        if (c >= r && c < r + ntl)
+          prm.xcl[c - r][r] = (T)h;
+        else if (h != 0.0)
+          ok = false;
+      }
+    for (int r = 0; ok && r < px->nr; ++r)
+      for (int c = 0; c < px->wr; ++c) {
+        const double h = px->h_band_r[r * px->wr + c];
+        if (c >= r && c < r + ntr)
+          prm.xcr[r + ntr - 1 - c][XV - px->nr + r] = (T)h;
+        else if (h != 0.0)
+          ok = false;
+      }
+    // the last tile must hold the three vectors that end at column n2 - 1
+    const int xl_last = ((n2 + G::TX - 1) / G::TX - 1) * G::TX;
+    if (n2 - xl_last < 3 * XV - G::HX) ok = false;
+    if (env_int("FDX_XBAND_SLOW", 0)) ok = false;
+    prm.xfast = ok ? 1 : 0, prm.xnt_l = ntl, prm.xnt_r = ntr;
+  }
   prm.z_begin = sl.z_begin, prm.z_end = sl.z_end;
-  prm.ablate = env_int("FDX_ABLATE", 0);
   prm.tz_off = -sl.in_first;
   prm.z_lo = 0, prm.z_hi = n0 - 1;
   for (int f = 0; f < Tr::NIN; ++f) {
@@ -833,6 +983,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     // small grids: keep at least ~2 waves of CTAs
     while (chunk > 4 * P && tiles * ((nz + chunk - 1) / chunk) < 2LL * kNumSMs * CFG::MINB) chunk /= 2;
   }
+  if (chunk > kMaxPlanes - 2 * P) chunk = kMaxPlanes - 2 * P;
   if (chunk > nz) chunk = nz;
   prm.chunk = chunk;
   prm.n_chunks = (nz + chunk - 1) / chunk;
@@ -873,6 +1024,15 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
       FDX_CFG(13, 16, 8, 2, 6, 4)
       FDX_CFG(14, 32, 8, 2, 6, 2)
       FDX_CFG(15, 16, 8, 2, 8, 3)
+      FDX_CFG(16, 16, 8, 2, 6, 4)
+      FDX_CFG(17, 16, 16, 2, 4, 2)
+      FDX_CFG(18, 16, 16, 2, 8, 2)
+      FDX_CFG(19, 16, 8, 2, 5, 5)
+      FDX_CFG(20, 16, 8, 1, 8, 6)
+      FDX_CFG(21, 16, 16, 1, 6, 3)
+      FDX_CFG(22, 32, 8, 2, 4, 2)
+      FDX_CFG(23, 16, 8, 2, 8, 4)
+      FDX_CFG(24, 16, 8, 1, 8, 8)
       default:
         break;
     }
@@ -928,6 +1088,7 @@ static int fused_radius(const fdx_plan_t plans[3], const T* const in[3], T* cons
   }
   if (plans[0]->nl < P || plans[0]->nr < P) return 0;
   if (plans[2]->n % V != 0) return 0;
+  if ((int64_t)plans[1]->n * plans[2]->n * (int64_t)sizeof(T) > 0x7fffffffLL) return 0;  // 32-bit plane stride (bytes) in the kernel
   for (int f = 0; f < Tr::NIN; ++f)
     if (((uintptr_t)in[f] & 15) != 0) return 0;
   for (int f = 0; f < Tr::NOUT; ++f)
