@@ -19,7 +19,8 @@ LIB = os.path.join(LIBDIR, "libfdx_b200.so")
 SOURCES = ("fdx_plan.cu", "fdx_axis.cu", "fdx_fused3d_lap.cu", "fdx_fused3d_div.cu", "fdx_fused3d_grad.cu", "fdx_fused3d_curl.cu")
 NVCC_FLAGS = [
     *(["-DFDX_SWEEP"] if os.environ.get("FDX_SWEEP") else []),
-    *(["-DFDX_ABLATION"] if os.environ.get("FDX_ABLATION") else []),
+    *([f"-DFDX_SWEEP_P={os.environ['FDX_SWEEP_P']}"] if os.environ.get("FDX_SWEEP_P") else []),
+    *([f"-DFDX_SWEEP_TSIZE={os.environ['FDX_SWEEP_TSIZE']}"] if os.environ.get("FDX_SWEEP_TSIZE") else []),
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",

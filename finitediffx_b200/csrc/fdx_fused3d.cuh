@@ -74,6 +74,8 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 constexpr int kTabMax = 640;   // band coefficients of all 6 sides, carried in the parameter block
 constexpr int kRowsMax = 96;   // band rows of all 6 sides
 constexpr int kMaxPlanes = 383;  // planes one CTA may march through (per-plane flag bytes in shared memory)
+constexpr int kMaxCuts = 128;    // z chunks per launch
+constexpr int kXTabMax = 320;    // x-band coefficients of both sides, staged in shared memory by the x-edge CTAs
 
 template <typename T>
 struct AxisDev {
@@ -93,7 +95,11 @@ struct FusedParams {
   int z_begin, z_end;  // output planes
   int z_lo, z_hi;      // addressable input planes [z_lo, z_hi]
   int tz_off;          // tensor-map plane index = global plane index + tz_off (= -in_first)
-  int chunk, n_chunks, tiles_x, tiles_y;
+  int n_chunks, tiles_x, tiles_y;
+  // z chunks in launch order (graded: long chunks first, short ones last so that the tail of the
+  // launch is made of short CTAs): first output plane and number of output planes of every chunk
+  int cut_z[kMaxCuts];
+  short cut_n[kMaxCuts];
   // fast x bands (band rows fit one 16-byte vector, taps fit three): per-tap coefficient vectors,
   // xcl[t][v] = tap t of left band row v (column v + t); xcr[t][v] = tap of right band row
   // v - (V - nr) that sits t columns before the row's own column
@@ -104,9 +110,13 @@ struct FusedParams {
   T tab[kTabMax];
 };
 
-template <int TXV_, int TYT_, int RY_, int STAGES_, int MINB_ = 1>
+// TXV x TYT threads own RY rows x one 16-byte vector each; a warp covers LX x (32 / LX) of them.  A narrow
+// warp (LX < TXV) keeps the x-band work of the first / last tile of a row inside fewer warps.
+template <int TXV_, int TYT_, int RY_, int STAGES_, int MINB_ = 1, int LX_ = 0>
 struct Cfg {
   static constexpr int TXV = TXV_, TYT = TYT_, RY = RY_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int LX = LX_ > 0 ? LX_ : (TXV_ < 32 ? TXV_ : 32);
+  static_assert(32 % LX == 0 && TXV_ % LX == 0 && TYT_ % (32 / LX) == 0 && LX >= RY_, "warp shape");
 };
 
 template <Op OP>
@@ -157,7 +167,9 @@ struct Geometry {
     for (int f = 0; f < Tr::NIN; ++f) b += box_x(f) * box_y(f) * (int)sizeof(T);
     return b;
   }
-  static constexpr int SMEM_BYTES = 640 + CFG::STAGES * STAGE_BYTES;  // barriers + plane flags + alignment slack
+  static constexpr int XTAB_BYTES = ((kXTabMax * (int)sizeof(T) + 127) / 128) * 128;
+  // barriers (128 B) + plane flags (384 B) + x-band table + alignment slack + stage ring
+  static constexpr int SMEM_BYTES = 512 + XTAB_BYTES + 128 + CFG::STAGES * STAGE_BYTES;
 };
 
 template <int N>
@@ -294,12 +306,11 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   using IP = InPlane<OP>;
   constexpr int V = G::V, RY = CFG::RY, WZ = G::WZ, STAGES = CFG::STAGES, HX = G::HX, HXV = G::HXV;
   constexpr int NY = IP::NY, NX = IP::NX;
-  constexpr int TRW = 32 / CFG::TXV;  // thread rows per warp
-  constexpr int WR = TRW * RY;        // grid rows per warp
+  constexpr int LX = CFG::LX, TRW = 32 / LX;  // a warp covers LX x TRW threads
+  constexpr int WR = TRW * RY;               // grid rows per warp
   // planes in flight: the stage refilled at step `it` was released at step it - (STAGES - LOOK), so
   // with LOOK = STAGES - 2 the issuing thread almost never waits for the slowest warp
   constexpr int LOOK = STAGES >= 4 ? STAGES - 2 : STAGES - 1;
-  static_assert(CFG::TXV == 16 || CFG::TXV == 32, "a warp must cover whole tile rows");
   static_assert(STAGES * 16 <= 128, "barrier area");
   using VT = Vec<T, V>;
 
@@ -308,8 +319,8 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // the stage ring rounded up to 128 B for TMA
   uint32_t smem0 = smem_u32(smem_raw);
   asm volatile("" : "+r"(smem0));  // opaque: computed once, kept in a register
-  const uint32_t ring = (smem0 + 512u + 127u) & ~127u;
-  const uint32_t bar_full = smem0, bar_empty = smem0 + 8u * STAGES, flag_base = smem0 + 128u;
+  const uint32_t ring = (smem0 + 512u + (uint32_t)G::XTAB_BYTES + 127u) & ~127u;
+  const uint32_t bar_full = smem0, bar_empty = smem0 + 8u * STAGES, flag_base = smem0 + 128u, xtab = smem0 + 512u;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -320,13 +331,10 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   const int tile_x = b % prm.tiles_x;
   b /= prm.tiles_x;
   const int tile_y = b % prm.tiles_y;
-  // launch order: the two chunks that touch the physical z boundary go first -- their one-sided
-  // planes are slow and must not form the tail of the launch
-  const int cslot = b / prm.tiles_y;
-  const int chunk = cslot == 0 ? 0 : (cslot == 1 ? prm.n_chunks - 1 : cslot - 1);
+  const int cslot = b / prm.tiles_y;  // chunks are listed in launch order (see launch_cfg)
   const int x0 = tile_x * G::TX, y0 = tile_y * G::TY;
-  const int zs = prm.z_begin + chunk * prm.chunk;
-  const int ze = min(prm.z_end, zs + prm.chunk);
+  const int zs = prm.cut_z[cslot];
+  const int ze = zs + prm.cut_n[cslot];
   const int zin0 = max(zs - P, prm.z_lo);
   const int zin1 = min(ze - 1 + P, prm.z_hi);
   const int n_planes = zin1 - zin0 + 1;
@@ -353,6 +361,16 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     const uint32_t f = (inr ? F_INR : 0u) | (emit ? F_EMIT : 0u) | (zb ? F_ZB : 0u) | ((inr && (edge || zb)) ? F_SLOW : 0u);
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(flag_base + (uint32_t)i), "r"(f) : "memory");
   }
+  if (xedge_l || xedge_r) {  // the dense x-band rows (left, then right) go to shared memory
+    const int cnt = prm.ax[2].nl * prm.ax[2].wl + prm.ax[2].nr * prm.ax[2].wr;  // <= kXTabMax, host-checked
+    for (int i = tid; i < cnt; i += G::NT) {
+      const T c = prm.tab[prm.ax[2].tab_l + i];
+      if constexpr (sizeof(T) == 4)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(xtab + 4u * (uint32_t)i), "f"(c) : "memory");
+      else
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(xtab + 8u * (uint32_t)i), "d"(c) : "memory");
+    }
+  }
   __syncthreads();
 
   // TMA issue (thread 0 only): plane `it` of this CTA's march goes to stage it % STAGES
@@ -371,7 +389,8 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     for (int it = 0; it < LOOK && it < n_planes; ++it) issue(it);
   }
 
-  const int tx = tid % CFG::TXV, ty = tid / CFG::TXV;
+  const int wrp = tid / 32;
+  const int tx = (wrp % (CFG::TXV / LX)) * LX + lane % LX, ty = (wrp / (CFG::TXV / LX)) * TRW + lane / LX;
   const int xg = x0 + tx * V;   // first global x of this thread's vector
   const int yg = y0 + ty * RY;  // first global y of this thread's rows
   const AxisDev<T>& A0 = prm.ax[0];
@@ -498,119 +517,117 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     return a;
   };
   // x bands, warp-cooperative: the band outputs of the WR grid rows of this warp are spread over
-  // the lanes, one element each -- lane = r + WR * (side * NBS + ob) handles the ob-th band column
-  // of `side` (0 left, 1 right) in warp row r, reading the tile in shared memory; the results travel
-  // back to the owning lanes with shuffles.  The host guarantees that the first (last) tile holds
-  // every left (right) band output and all of its taps.
-  constexpr int NBS = (32 / WR) / 2;  // band columns per side and pass
-  // per owned element: 0x80 | band column index, packed one byte per vector element
-  uint32_t xb_desc = 0;
-  if (xedge_l || xedge_r) {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int x = xg + v;
-      uint32_t d = 0;
-      if (xedge_l && x < A2.nl) d = 0x80u | (uint32_t)x;
-      if (xedge_r && x >= n2 - A2.nr && x < n2) d = 0xC0u | (uint32_t)(x - (n2 - A2.nr));  // 0x40: right side
-      xb_desc |= d << (8 * v);
-    }
-  }
-  auto xband_fix = [&](const T* tilef, int pitch, int yo, VT (&xs)[RY]) {
-    const int wrow0 = (tid / 32) * WR;  // first tile row of this warp
-    const int r = lane % WR, slot = lane / WR;
-    const int side = slot / NBS, obl = slot % NBS;
-    const int nb = side ? (xedge_r ? A2.nr : 0) : (xedge_l ? A2.nl : 0);
-    const int nbmax = max(xedge_l ? A2.nl : 0, xedge_r ? A2.nr : 0);
-    const T* src0 = tilef + (wrow0 + r + yo) * pitch - (x0 - HX);  // address of global column 0 of this row
-    const bool row_in = y0 + wrow0 + r < n1;
+  // the lanes, one element each -- lane = r + WR * bl evaluates band column b0 + bl of warp row r
+  // from the tile in shared memory (scalar loads, coefficients from the table staged at `xtab`, taps
+  // in ascending column order like the reference's sum); the results travel to the lanes that own
+  // those elements with shuffles.  The host guarantees that the first (last) tile holds every left
+  // (right) band output and all of its taps.  `row0` = shared address of tile column 0 of the tile
+  // row that holds grid row y0 of this field.
+  constexpr int NB = 32 / WR;  // band columns per pass
+  auto lds_s = [&](uint32_t a) {
+    T r;
+    if constexpr (sizeof(T) == 4)
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+    else
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
+    return r;
+  };
+  auto xband_coop = [&](uint32_t row0, int pitch, VT (&xs)[RY]) {
+    const int r = lane % WR, bl = lane / WR;
+    const uint32_t rowa = row0 + (uint32_t)(((ty / TRW) * WR + r) * pitch * (int)sizeof(T));
     const int myrow = (ty % TRW) * RY;
-    for (int ob0 = 0; ob0 < nbmax; ob0 += NBS) {  // one pass unless a band is wider than NBS
-      const int ob = ob0 + obl;
-      T val = 0;
-      if (ob < nb && row_in) {
-        const int x = side ? (n2 - A2.nr + ob) : ob;
-        int tab, c0, c1, cb;
-        band_rng(A2, x, tab, c0, c1, cb);
-        const T* src = src0 + cb;
-        T a = 0;
-        for (int c = c0; c < c1; c += 4) {
-          T cf[4], xv[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int cc = min(c + q, c1 - 1);
-            cf[q] = prm.tab[tab + cc];
-            if (c + q >= c1) cf[q] = 0;
-            xv[q] = src[cc];
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      if (!(side ? xedge_r : xedge_l)) continue;
+      const int nb = side ? A2.nr : A2.nl, w = side ? A2.wr : A2.wl;
+      const int tab0 = side ? A2.nl * A2.wl : 0;          // first coefficient of this side in the table
+      const int col0 = (side ? n2 - A2.wr : 0) - (x0 - HX);  // tile column of band column 0
+      const int xb0 = side ? n2 - A2.nr : 0;              // global x of band row 0
+#pragma unroll 1
+      for (int b0 = 0; b0 < nb; b0 += NB) {
+        const int b = b0 + bl;
+        T val = 0;
+        if (b < nb) {
+          const short2 rg = prm.rng[(side ? A2.rng_r : A2.rng_l) + b];
+          uint32_t ca = xtab + (uint32_t)((tab0 + b * w + rg.x) * (int)sizeof(T));
+          uint32_t xa_ = rowa + (uint32_t)((col0 + rg.x) * (int)sizeof(T));
+          T a = 0;
+#pragma unroll 2
+          for (int c = rg.x; c < rg.y; ++c) {
+            a = fma(lds_s(ca), lds_s(xa_), a);
+            ca += (uint32_t)sizeof(T), xa_ += (uint32_t)sizeof(T);
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) a = fma(cf[q], xv[q], a);
+          val = a * A2.alpha;
         }
-        val = a * A2.alpha;
-      }
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const uint32_t d = (xb_desc >> (8 * v)) & 0xffu;
-        const int obx = (int)(d & 0x3fu) - ob0;
-        const bool mine = (d & 0x80u) && obx >= 0 && obx < NBS;
-        const int col = WR * (((d & 0x40u) ? NBS : 0) + (mine ? obx : 0));
+        for (int v = 0; v < V; ++v) {
+          const int bb = xg + v - xb0 - b0;  // band column of this element relative to the pass
+          const bool mine = bb >= 0 && bb < NB && bb + b0 < nb && xg < n2;
+          const int col = WR * (mine ? bb : 0);
 #pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          const T got = __shfl_sync(0xffffffffu, val, (myrow + j + col) & 31);
-          if (mine) xs[j].v[v] = got;
+          for (int j = 0; j < RY; ++j) {
+            const T got = __shfl_sync(0xffffffffu, val, (myrow + j + col) & 31);
+            if (mine) xs[j].v[v] = got;
+          }
         }
       }
     }
   };
-  // x bands, fast form (prm.xfast): every band row of a side lies in ONE thread's vector and its taps
-  // in three vectors, so the edge thread evaluates them from registers with static indices; the
-  // taps run in ascending column order like the reference's sum
+  // x bands, fast form (prm.xfast): every band row of a side lies in ONE thread's vector (the owner,
+  // tx = 0 on the left, the last valid vector on the right) and its taps in three vectors, so they are
+  // evaluated from registers with static indices, taps in ascending column order like the reference's
+  // sum.  The owner's RY rows are spread over RY neighbouring lanes (helper h takes row h) and come
+  // back with shuffles, so a warp pays for one row, not RY.
   const bool xfast = prm.xfast != 0;
-  const bool xmine_l = xedge_l && tx == 0, xmine_r = xedge_r && xg == n2 - V;
-  auto xband_fast = [&](uint32_t row /* shared address of this thread's vector in the row */, VT (&x)) {
+  auto xband_fast = [&](uint32_t row /* shared address of this thread's vector in the row of yg */, int pitch, VT (&xs)[RY]) {
     constexpr int XT = FusedParams<T>::kXT;
-    if (xmine_l) {
-      T w[3 * V];
 #pragma unroll
-      for (int h = 0; h < 3; ++h) {
-        const VT t = lds_vec<T, V>(row + (uint32_t)(h * V * sizeof(T)));
+    for (int side = 0; side < 2; ++side) {
+      if (!(side ? xedge_r : xedge_l)) continue;  // CTA-uniform
+      const int txo = side ? (n2 - V - x0) / V : 0;  // the owner's tx
+      const int h = side ? txo - tx : tx;             // this lane helps with row h of the owner
+      T val[V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) w[h * V + v] = t.v[v];
+      for (int v = 0; v < V; ++v) val[v] = 0;
+      if (h >= 0 && h < RY) {
+        // the owner's vector in row h, and the two vectors towards the interior
+        const uint32_t base = row + (uint32_t)(((txo - tx) * V + h * pitch) * (int)sizeof(T));
+        T w[3 * V];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const VT t = lds_vec<T, V>(side ? base - (uint32_t)((2 - g) * V * sizeof(T)) : base + (uint32_t)(g * V * sizeof(T)));
+#pragma unroll
+          for (int v = 0; v < V; ++v) w[g * V + v] = t.v[v];
+        }
+        if (side == 0) {
+#pragma unroll
+          for (int t = 0; t < XT; ++t) {
+            if (t < prm.xnt_l) {
+#pragma unroll
+              for (int v = 0; v < V; ++v) val[v] = fma(prm.xcl[t][v], w[v + t], val[v]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int t = XT - 1; t >= 0; --t) {
+            if (t < prm.xnt_r) {
+#pragma unroll
+              for (int v = 0; v < V; ++v) val[v] = fma(prm.xcr[t][v], w[2 * V + v - t], val[v]);
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) val[v] *= A2.alpha;
       }
-      T a[V];
+      const bool owner = tx == txo;
 #pragma unroll
-      for (int v = 0; v < V; ++v) a[v] = 0;
+      for (int j = 0; j < RY; ++j) {
 #pragma unroll
-      for (int t = 0; t < XT; ++t) {
-        if (t < prm.xnt_l) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) a[v] = fma(prm.xcl[t][v], w[v + t], a[v]);
+        for (int v = 0; v < V; ++v) {
+          const T got = j == 0 ? val[v] : __shfl_sync(0xffffffffu, val[v], (lane + (side ? -j : j)) & 31);
+          if (owner && (side ? v >= V - A2.nr : v < A2.nl)) xs[j].v[v] = got;
         }
       }
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (v < A2.nl) x.v[v] = a[v] * A2.alpha;
-    }
-    if (xmine_r) {
-      T w[3 * V];
-#pragma unroll
-      for (int h = 0; h < 3; ++h) {
-        const VT t = lds_vec<T, V>(row - (uint32_t)((2 - h) * V * sizeof(T)));
-#pragma unroll
-        for (int v = 0; v < V; ++v) w[h * V + v] = t.v[v];
-      }
-      T a[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) a[v] = 0;
-#pragma unroll
-      for (int t = XT - 1; t >= 0; --t) {
-        if (t < prm.xnt_r) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) a[v] = fma(prm.xcr[t][v], w[2 * V + v - t], a[v]);
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-        if (v >= V - A2.nr) x.v[v] = a[v] * A2.alpha;
     }
   };
   // z band of plane z (always from global memory: the other planes are not in the ring)
@@ -731,13 +748,9 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
           for (int qq = 0; qq < NX; ++qq) {
             const int f = IP::xfield(qq);
             if (xfast) {
-              if (xmine_l || xmine_r) {
-#pragma unroll
-                for (int j = 0; j < RY; ++j)
-                  xband_fast(tb[f] + soff + (uint32_t)((G::yoff(f) + j) * G::box_x(f) * sizeof(T)), xa[qq][j]);
-              }
+              xband_fast(tb[f] + soff + (uint32_t)(G::yoff(f) * G::box_x(f) * sizeof(T)), G::box_x(f), xa[qq]);
             } else {
-              xband_fix(tile(f), G::box_x(f), G::yoff(f), xa[qq]);
+              xband_coop(ring + soff + G::field_off(f) + (uint32_t)(G::yoff(f) * G::box_x(f) * sizeof(T)), G::box_x(f), xa[qq]);
             }
           }
         }
@@ -952,6 +965,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     // the last tile must hold the three vectors that end at column n2 - 1
     const int xl_last = ((n2 + G::TX - 1) / G::TX - 1) * G::TX;
     if (n2 - xl_last < 3 * XV - G::HX) ok = false;
+    if (((n2 - xl_last) / XV - 1) % CFG::LX < CFG::RY - 1) ok = false;  // the helper lanes sit in the owner's warp
     if (env_int("FDX_XBAND_SLOW", 0)) ok = false;
     prm.xfast = ok ? 1 : 0, prm.xnt_l = ntl, prm.xnt_r = ntr;
   }
@@ -970,23 +984,56 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     const fdx_plan_s* px = plans[2];
     const int xl = (prm.tiles_x - 1) * G::TX;
     if (px->nl > G::TX || px->wl > G::TX + G::HX || n2 - xl < px->nr || xl > n2 - px->wr + G::HX) return FDX_EUNSUPPORTED;
-    if (px->nl > 63 || px->nr > 63) return FDX_EUNSUPPORTED;
+    if (px->nl * px->wl + px->nr * px->wr > kXTabMax) return FDX_EUNSUPPORTED;
   }
   const int nz = sl.z_end - sl.z_begin;
   const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
-  // z chunking: enough CTAs for a few waves, but chunks long enough to amortise the 2P warm-up planes
-  // z chunking: many short CTAs beat few long ones on B200 (dynamic scheduling hides the slow
-  // boundary tiles); 32 planes amortise the 2P warm-up planes of every chunk well enough
-  int chunk = env_int("FDX_FUSED_CHUNK", 0);
-  if (chunk <= 0) {
-    chunk = 32 > 8 * P ? 32 : 8 * P;
+  // z chunking.  Every chunk pays 2P warm-up planes, so long chunks are cheaper, but the launch ends
+  // when its last CTA does: the chunks are graded -- long ones first, then medium, and the CTAs of the
+  // last ~1.5 waves are short -- which keeps both the redundancy and the tail small.
+  {
+    const int64_t slots = (int64_t)kNumSMs * CFG::MINB;
+    int L = env_int("FDX_FUSED_CHUNK", 0), S = env_int("FDX_FUSED_CHUNK_SHORT", 0);
+    const bool uniform = L > 0 && S <= 0;  // an explicit chunk alone means uniform chunks (sweeps)
+    if (L <= 0) L = 64 > 8 * P ? 64 : 8 * P;
+    if (S <= 0) S = 16 > 4 * P ? 16 : 4 * P;
+    if (uniform) S = L;
+    if (L > kMaxPlanes - 2 * P) L = kMaxPlanes - 2 * P;
+    if (S > L) S = L;
+    if ((int64_t)nz > (int64_t)L * (kMaxCuts - 28)) L = (int)((nz + kMaxCuts - 29) / (kMaxCuts - 28));
+    if (L > kMaxPlanes - 2 * P) return FDX_EUNSUPPORTED;
     // small grids: keep at least ~2 waves of CTAs
-    while (chunk > 4 * P && tiles * ((nz + chunk - 1) / chunk) < 2LL * kNumSMs * CFG::MINB) chunk /= 2;
+    while (!uniform && L > S && tiles * ((nz + L - 1) / L) < 2 * slots) L = L / 2 > S ? L / 2 : S;
+    while (!uniform && S > 4 * P && tiles * ((nz + S - 1) / S) < 2 * slots) S /= 2;
+    if (S > L) S = L;
+    // sizes from the end of the z range backwards: short layers, as many medium ones, then long ones
+    int sizes[kMaxCuts];
+    int n = 0, rem = nz;
+    int n_short = (int)((3 * slots + 2 * tiles - 1) / (2 * tiles));  // ~1.5 waves of CTAs
+    if (n_short > 12) n_short = 12;
+    if (uniform || L == S) n_short = 0;
+    for (int i = 0; i < n_short && rem > nz / 2 && rem > S; ++i) sizes[n++] = S, rem -= S;
+    const int M = 2 * S < L ? 2 * S : L;
+    for (int i = 0; i < n_short && M < L && rem > nz / 2 && rem > M; ++i) sizes[n++] = M, rem -= M;
+    if (rem > 0) {
+      const int nl = (rem + L - 1) / L;
+      for (int i = 0; i < nl; ++i) {
+        const int sz = (rem + (nl - i) - 1) / (nl - i);
+        sizes[n++] = sz, rem -= sz;
+      }
+    }
+    if (n > kMaxCuts) return FDX_EUNSUPPORTED;
+    // launch order: the first chunk, the last one (both touch the physical boundary, whose one-sided
+    // planes are slow), then the others in z order -- long to short
+    int zstart[kMaxCuts], zlen[kMaxCuts];
+    int z = sl.z_begin;
+    for (int i = n - 1, k = 0; i >= 0; --i, ++k) zstart[k] = z, zlen[k] = sizes[i], z += sizes[i];
+    int k = 0;
+    prm.cut_z[k] = zstart[0], prm.cut_n[k] = (short)zlen[0], ++k;
+    if (n > 1) prm.cut_z[k] = zstart[n - 1], prm.cut_n[k] = (short)zlen[n - 1], ++k;
+    for (int i = 1; i + 1 < n; ++i) prm.cut_z[k] = zstart[i], prm.cut_n[k] = (short)zlen[i], ++k;
+    prm.n_chunks = n;
   }
-  if (chunk > kMaxPlanes - 2 * P) chunk = kMaxPlanes - 2 * P;
-  if (chunk > nz) chunk = nz;
-  prm.chunk = chunk;
-  prm.n_chunks = (nz + chunk - 1) / chunk;
   const int64_t blocks = tiles * prm.n_chunks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   auto kern = fused3d_kernel<OP, T, P, CFG>;
@@ -1007,7 +1054,13 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
   case ID:               \
     return launch_cfg<OP, T, P, Cfg<__VA_ARGS__>>(plans, in, out, alpha, sl, st);
 #ifdef FDX_SWEEP
-  if constexpr (sizeof(T) == 4 && (P == 3 || P == 2)) {
+#ifndef FDX_SWEEP_TSIZE
+#define FDX_SWEEP_TSIZE 4
+#endif
+#ifndef FDX_SWEEP_P
+#define FDX_SWEEP_P 3
+#endif
+  if constexpr (sizeof(T) == FDX_SWEEP_TSIZE && P == FDX_SWEEP_P) {
     switch (cfg) {
       FDX_CFG(1, 16, 16, 2, 4, 1)
       FDX_CFG(2, 16, 16, 2, 4, 2)
@@ -1033,6 +1086,24 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
       FDX_CFG(22, 32, 8, 2, 4, 2)
       FDX_CFG(23, 16, 8, 2, 8, 4)
       FDX_CFG(24, 16, 8, 1, 8, 8)
+      FDX_CFG(25, 16, 8, 2, 8, 4, 8)
+      FDX_CFG(26, 16, 8, 2, 6, 4, 8)
+      FDX_CFG(27, 16, 8, 2, 8, 3, 8)
+      FDX_CFG(28, 16, 16, 2, 4, 2, 8)
+      FDX_CFG(29, 32, 8, 2, 4, 2, 8)
+      FDX_CFG(30, 16, 8, 2, 8, 4, 4)
+      FDX_CFG(31, 16, 32, 1, 4, 1)
+      FDX_CFG(32, 16, 16, 1, 4, 2)
+      FDX_CFG(33, 16, 16, 1, 6, 3)
+      FDX_CFG(34, 16, 8, 1, 8, 4)
+      FDX_CFG(35, 16, 8, 1, 8, 6)
+      FDX_CFG(36, 16, 16, 2, 4, 1)
+      FDX_CFG(37, 16, 8, 2, 4, 3)
+      FDX_CFG(38, 16, 8, 2, 6, 2)
+      FDX_CFG(39, 32, 8, 1, 4, 3)
+      FDX_CFG(40, 32, 8, 2, 4, 2)
+      FDX_CFG(41, 16, 8, 1, 8, 5, 8)
+      FDX_CFG(42, 16, 16, 1, 6, 3, 8)
       default:
         break;
     }
@@ -1065,7 +1136,7 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
     switch (cfg) {
       FDX_CFG(1, 16, 16, 2, 4, 2)
       default:
-        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 8, 3>>(plans, in, out, alpha, sl, st);
+        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 8, 4, 8>>(plans, in, out, alpha, sl, st);
     }
   }
 #undef FDX_CFG

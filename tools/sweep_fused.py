@@ -20,7 +20,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 dtype = torch.float64 if (len(sys.argv) > 3 and sys.argv[3] == "f64") else torch.float32
 acc = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 cfgs = [int(c) for c in os.environ.get("SWEEP_CFGS", "0,1,2,3,4,5,6,7,8,9,10,11").split(",")]
-chunks = [int(c) for c in os.environ.get("SWEEP_CHUNKS", "0,32,64,128").split(",")]
+chunks = os.environ.get("SWEEP_CHUNKS", "0,32,64,128").split(",")  # "L" (uniform) or "L:S" (graded long:short)
 
 dev = torch.device("cuda")
 fields_in = 3 if op in ("divergence", "curl") else 1
@@ -47,7 +47,8 @@ results = []
 for cfg in cfgs:
     for chunk in chunks:
         os.environ["FDX_FUSED_CFG"] = str(cfg)
-        os.environ["FDX_FUSED_CHUNK"] = str(chunk)
+        os.environ["FDX_FUSED_CHUNK"] = str(chunk).split(":")[0]
+        os.environ["FDX_FUSED_CHUNK_SHORT"] = str(chunk).split(":")[1] if ":" in str(chunk) else "0"
         try:
             out = call(xs[0])
             torch.cuda.synchronize()
