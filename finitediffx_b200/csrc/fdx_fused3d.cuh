@@ -539,6 +539,10 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
       if (!(side ? xedge_r : xedge_l)) continue;
+      {  // warp-uniform: a warp whose columns hold no band element of this side has nothing to do
+        const int wx0 = x0 + (wrp % (CFG::TXV / LX)) * LX * V;
+        if (side ? (wx0 + LX * V <= n2 - A2.nr) : (wx0 >= A2.nl)) continue;
+      }
       const int nb = side ? A2.nr : A2.nl, w = side ? A2.wr : A2.wl;
       const int tab0 = side ? A2.nl * A2.wl : 0;          // first coefficient of this side in the table
       const int col0 = (side ? n2 - A2.wr : 0) - (x0 - HX);  // tile column of band column 0
@@ -1109,34 +1113,27 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
     }
   }
 #endif
-  // defaults from the round-1 sweeps on B200 (tools/sweep_fused.py, profiles/): 64x16-point tiles,
-  // 128 threads, 8 TMA stages, 3 CTAs per SM for the light operators
-  constexpr bool heavy = (OP == CURL) || (sizeof(T) == 8 && P >= 3) || (P >= 5);
-  constexpr bool wide = P >= 5;  // 11/13-tap queues: one row per thread, taller tiles for the halo ratio
-  if constexpr (wide) {
+  // defaults from the sweeps on B200 (tools/sweep_fused.py, profiles/): 64x16-point tiles of 128
+  // threads everywhere; the fp32 laplacian (most arithmetic per byte) runs 4 CTAs per SM with 8 TMA
+  // stages and narrow warps, curl (two queues, three inputs) one row per thread
+  if constexpr (OP == CURL) {
     switch (cfg) {
-      FDX_CFG(1, 16, 16, 1, 4, 2)
+      FDX_CFG(1, 16, 8, 2, 4, 3)
       default:
-        return launch_cfg<OP, T, P, Cfg<16, 32, 1, 4, 1>>(plans, in, out, alpha, sl, st);
+        // two register queues: from radius 4 on they need more than 128 registers
+        return launch_cfg<OP, T, P, Cfg<16, 16, 1, 4, (P <= 3 ? 2 : 1)>>(plans, in, out, alpha, sl, st);
     }
-  } else if constexpr (heavy) {
+  } else if constexpr (OP == LAP && sizeof(T) == 4 && P <= 3) {
     switch (cfg) {
-      FDX_CFG(1, 16, 16, 1, 4, 1)
+      FDX_CFG(1, 16, 8, 2, 4, 3)
       default:
-        return launch_cfg<OP, T, P, Cfg<16, 16, 1, 4, 2>>(plans, in, out, alpha, sl, st);
-    }
-  } else if constexpr (OP == DIV) {
-    // divergence carries one 2P+1 queue for three inputs: 4 rows per thread amortise the per-step cost
-    switch (cfg) {
-      FDX_CFG(1, 16, 8, 2, 8, 3)
-      default:
-        return launch_cfg<OP, T, P, Cfg<16, 8, 4, 4, 2>>(plans, in, out, alpha, sl, st);
+        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 8, 4, 8>>(plans, in, out, alpha, sl, st);
     }
   } else {
     switch (cfg) {
-      FDX_CFG(1, 16, 16, 2, 4, 2)
+      FDX_CFG(1, 16, 16, 1, 4, 2)
       default:
-        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 8, 4, 8>>(plans, in, out, alpha, sl, st);
+        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 4, 3>>(plans, in, out, alpha, sl, st);
     }
   }
 #undef FDX_CFG

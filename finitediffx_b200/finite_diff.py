@@ -292,7 +292,7 @@ def difference(
         raise ValueError("difference needs an array with at least one axis")
     ax = _norm_axis(axis, x.ndim)
     term = Term(0, 0, ax, int(derivative), int(accuracy), method, _alpha(step_size, derivative))
-    return restore(_run(x.unsqueeze(0), [term], 1)[0])
+    return restore(_run(x.unsqueeze(0), [term], 1).squeeze(0))  # (a view both ways: select would cost a zero-fill in backward)
 
 
 def gradient(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
@@ -348,7 +348,7 @@ def divergence(array, *, accuracy=1, step_size=1, keepdims: bool = True, method:
     if x.shape[0] < nd:
         raise IndexError(f"index {x.shape[0]} is out of bounds for axis 0 with size {x.shape[0]}")
     out = _run(x, terms, 1)
-    return restore(out if keepdims else out[0])
+    return restore(out if keepdims else out.squeeze(0))
 
 
 def hessian(array, *, accuracy=2, step_size=1, method: MethodKind = "central"):
@@ -386,7 +386,7 @@ def laplacian(array, *, accuracy=1, step_size=1, method: MethodKind = "central")
     accuracy = _check_and_return(accuracy, x.ndim, "accuracy")
     step_size = _check_and_return(step_size, x.ndim, "step_size")
     terms = [Term(0, 0, k, 2, int(a), method, _alpha(h, 2)) for k, (a, h) in enumerate(zip(accuracy, step_size))]
-    return restore(_run(x.unsqueeze(0), terms, 1)[0])
+    return restore(_run(x.unsqueeze(0), terms, 1).squeeze(0))
 
 
 def curl(array, *, accuracy=1, step_size=1, method: MethodKind = "central", keepdims: bool = True):
@@ -416,7 +416,7 @@ def curl(array, *, accuracy=1, step_size=1, method: MethodKind = "central", keep
         return restore(_run(x, terms, 3))
     if x.ndim == 3 and x.shape[0] == 2:
         out = _run(x, [term(0, 1, 0, +1), term(0, 0, 1, -1)], 1)
-        return restore(out if keepdims else out[0])
+        return restore(out if keepdims else out.squeeze(0))
     raise ValueError(
         f"`curl` is only implemented for 2D and 3D vector fields, got array.ndim={x.ndim}"
         "for 2D vector fields, the leading axis must have a shape=2, "
