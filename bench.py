@@ -336,8 +336,9 @@ def run_ours(args):
     if world == 1:
         hx = [torch.empty(inputs[0].shape, dtype=inputs[0].dtype, pin_memory=True).copy_(inputs[i]) for i in range(2)]
         e_steps = max(3, min(args.steps, 10))
-        for i in range(2):
-            _call(fdx, w, hx[i % 2])
+        r = None
+        for i in range(3):  # warm-up as the timed loop runs: the previous result stays alive while the next
+            r = _call(fdx, w, hx[i % 2])  # one is produced, so both pinned result blocks exist before timing
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(e_steps):

@@ -12,7 +12,8 @@ derivative along axis 0 crosses a cut, so each operator call needs ONE neighbour
 Halo planes are contiguous in a C-ordered array, so they are sent in place (no packing) with NCCL
 point-to-point send/recv between neighbours, on a communication stream.  The fused kernel for the
 planes that do not depend on a halo ([z0+P, z1-P)) runs concurrently on the compute stream; the two
-P-plane shells next to the cuts follow once the exchange has landed.  Ranks at the physical ends of
+P-plane shells next to the cuts are launched on a third stream behind the halo event, so they fill
+the tail of the interior kernel.  Ranks at the physical ends of
 the grid keep the reference's one-sided boundary stencils: every rank addresses planes by their
 GLOBAL index (finitediffx_b200/slab.py), so the boundary logic is the single-GPU one.
 """
@@ -84,9 +85,9 @@ class SlabOperator:
     """A fused operator on a slab-decomposed global grid.
 
     Device buffers (per rotating buffer set): inputs [P halo | owned | P halo] planes, outputs
-    [owned] planes.  ``step(b)`` = halo exchange (comm stream) overlapped with the interior kernel,
-    then the two shells.  Requires owned >= 2P and, on the end ranks, owned >= the width of the
-    one-sided boundary band."""
+    [owned] planes.  ``step(b)`` = halo exchange (comm stream) overlapped with the interior kernel;
+    the two shells run on a third stream as soon as the halos have landed.  Requires owned >= 2P
+    and, on the end ranks, owned >= the width of the one-sided boundary band."""
 
     def __init__(self, sl: Slab, kind: str, spatial: Sequence[int], dtype: torch.dtype, *, accuracy: int, step_size,
                  device: torch.device, method: str = "central", n_buffers: int = 1):
@@ -104,6 +105,10 @@ class SlabOperator:
         self.outputs = [[torch.empty((self.owned, n1, n2), dtype=dtype, device=device) for _ in range(nout)] for _ in range(n_buffers)]
         self.comm = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.ev_halo = torch.cuda.Event() if device.type == "cuda" else None
+        # the two shells run on their own stream: they become runnable as soon as the halos have landed
+        # and fill the tail of the interior kernel instead of following it
+        self.shell = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.ev_shell = torch.cuda.Event() if device.type == "cuda" else None
         self.halo_bytes_per_step = 0
 
     # -- data access -----------------------------------------------------------------------
@@ -135,11 +140,16 @@ class SlabOperator:
         # planes that need no halo: everything except P planes next to each cut
         lo = z0 + (P if sl.lower is not None else 0)
         hi = z1 - (P if sl.upper is not None else 0)
+        if has_nb:
+            self.shell.wait_stream(cur)  # (before the interior launch: only the inputs of this step)
         _slab.run_slab(self.spec, ins, z0 - P, outs, z0, lo, hi)
         if has_nb:
-            cur.wait_event(self.ev_halo)
-            if sl.lower is not None:
-                _slab.run_slab(self.spec, ins, z0 - P, outs, z0, z0, lo)
-            if sl.upper is not None:
-                _slab.run_slab(self.spec, ins, z0 - P, outs, z0, hi, z1)
+            with torch.cuda.stream(self.shell):
+                self.shell.wait_event(self.ev_halo)
+                if sl.lower is not None:
+                    _slab.run_slab(self.spec, ins, z0 - P, outs, z0, z0, lo, stream=self.shell)
+                if sl.upper is not None:
+                    _slab.run_slab(self.spec, ins, z0 - P, outs, z0, hi, z1, stream=self.shell)
+                self.ev_shell.record(self.shell)
+            cur.wait_event(self.ev_shell)
         return outs
