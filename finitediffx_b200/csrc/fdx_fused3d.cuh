@@ -1026,6 +1026,23 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
         sizes[n++] = sz, rem -= sz;
       }
     }
+    if (const char* cuts = std::getenv("FDX_FUSED_CUTS")) {  // experiments: explicit sizes, last z chunk first
+      n = 0, rem = nz;
+      for (const char* c = cuts; *c && rem > 0 && n < kMaxCuts - 1;) {
+        int v = std::atoi(c);
+        if (v <= 0) break;
+        if (v > kMaxPlanes - 2 * P) v = kMaxPlanes - 2 * P;
+        if (v > rem) v = rem;
+        sizes[n++] = v, rem -= v;
+        while (*c && *c != ',') ++c;
+        if (*c == ',') ++c;
+      }
+      while (rem > 0 && n < kMaxCuts) {
+        const int v = rem < L ? rem : L;
+        sizes[n++] = v, rem -= v;
+      }
+      if (rem > 0) return FDX_EUNSUPPORTED;
+    }
     if (n > kMaxCuts) return FDX_EUNSUPPORTED;
     // launch order: the first chunk, the last one (both touch the physical boundary, whose one-sided
     // planes are slow), then the others in z order -- long to short
