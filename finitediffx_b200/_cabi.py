@@ -246,30 +246,43 @@ def _slab(slab):
     return C.byref(slab) if slab is not None else None
 
 
+_launch_memo: dict = {}
+
+
+def _launch_args(kind: str, plans: Sequence[AxisPlan], alpha: Sequence[float], sfx: str, dev):
+    """Per-(operator, plans, alpha, dtype, device) constants of a fused launch: the entry point, the
+    plan-handle array and the alpha array (ctypes objects are built once, not per call)."""
+    key = (kind, tuple(id(p) for p in plans), tuple(alpha), sfx, dev.index)
+    hit = _launch_memo.get(key)
+    if hit is None or any(a is not b for a, b in zip(hit[0], plans)):
+        keep, hp = _handles(plans, dev)
+        hit = (tuple(plans), keep, hp, _alphas(alpha), getattr(load(), f"fdx_{kind}3d_{sfx}"))
+        if len(_launch_memo) > 512:
+            _launch_memo.clear()
+        _launch_memo[key] = hit
+    return hit
+
+
 def fused3d(kind: str, plans: Sequence[AxisPlan], xs, outs, alpha: Sequence[float], slab: "Slab | None" = None) -> int:
     """Call one of the fused 3-D entry points.  ``xs`` / ``outs`` are a tensor (scalar field) or a
     sequence of three tensors (vector field components).  Returns the library's status code for
     FDX_EUNSUPPORTED so callers can fall back to ``axis_apply``; raises on any other error."""
-    first = xs if isinstance(xs, torch.Tensor) else xs[0]
+    x_one, o_one = isinstance(xs, torch.Tensor), isinstance(outs, torch.Tensor)
+    first = xs if x_one else xs[0]
     dev = first.device
-    for t in ([xs] if isinstance(xs, torch.Tensor) else list(xs)) + ([outs] if isinstance(outs, torch.Tensor) else list(outs)):
-        _require(t, "tensor")
-    keep, hp = _handles(plans, dev)
-    sfx = _sfx(first)
-    st = _stream_ptr(dev)
-    lib = load()
+    for t in ((xs,) if x_one else xs):
+        if not (t.is_cuda and t.is_contiguous()):
+            _require(t, "tensor")
+    for t in ((outs,) if o_one else outs):
+        if not (t.is_cuda and t.is_contiguous()):
+            _require(t, "tensor")
+    if kind not in ("laplacian", "divergence", "gradient", "curl"):
+        raise ValueError(kind)
+    _, _, hp, al, fn = _launch_args(kind, plans, alpha, _sfx(first), dev)
+    xin = C.c_void_p(xs.data_ptr()) if x_one else _ptrs(xs)
+    xout = C.c_void_p(outs.data_ptr()) if o_one else _ptrs(outs)
     with _on_device(dev):
-        if kind == "laplacian":
-            rc = getattr(lib, f"fdx_laplacian3d_{sfx}")(hp, C.c_void_p(xs.data_ptr()), C.c_void_p(outs.data_ptr()), _alphas(alpha), _slab(slab), st)
-        elif kind == "divergence":
-            rc = getattr(lib, f"fdx_divergence3d_{sfx}")(hp, _ptrs(xs), C.c_void_p(outs.data_ptr()), _alphas(alpha), _slab(slab), st)
-        elif kind == "gradient":
-            rc = getattr(lib, f"fdx_gradient3d_{sfx}")(hp, C.c_void_p(xs.data_ptr()), _ptrs(outs), _alphas(alpha), _slab(slab), st)
-        elif kind == "curl":
-            rc = getattr(lib, f"fdx_curl3d_{sfx}")(hp, _ptrs(xs), _ptrs(outs), _alphas(alpha), _slab(slab), st)
-        else:
-            raise ValueError(kind)
-    del keep
+        rc = fn(hp, xin, xout, al, _slab(slab), _stream_ptr(dev))
     if rc == -2:  # FDX_EUNSUPPORTED
         return rc
     check(rc, f"fdx_{kind}3d")

@@ -24,6 +24,7 @@
 // back -- inside the library, still on the GPU -- to the composition of axis kernels.
 #include <cuda.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 #include <type_traits>
@@ -1008,7 +1009,10 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     if (L > kMaxPlanes - 2 * P) return FDX_EUNSUPPORTED;
     // small grids: keep at least ~2 waves of CTAs
     while (!uniform && L > S && tiles * ((nz + L - 1) / L) < 2 * slots) L = L / 2 > S ? L / 2 : S;
-    while (!uniform && S > 4 * P && tiles * ((nz + S - 1) / S) < 2 * slots) S /= 2;
+    // ... and tiny grids are latency-bound (a march is a serial chain of ~1 us per plane, measured
+    // 35 -> 16 us for the README's 100^3 divergence): many very short chunks until two waves are filled
+    if (!uniform && L == S)
+      while (S > 4 && tiles * ((nz + S - 1) / S) < 2 * slots) S = L = (S / 2 > 4 ? S / 2 : 4);
     if (S > L) S = L;
     // sizes from the end of the z range backwards: short layers, as many medium ones, then long ones
     int sizes[kMaxCuts];
@@ -1058,8 +1062,18 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
   const int64_t blocks = tiles * prm.n_chunks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   auto kern = fused3d_kernel<OP, T, P, CFG>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
-  if (e != cudaSuccess) return (int)e;
+  {
+    // once per kernel instantiation and device (the attribute is per device; 16 devices at most)
+    static std::atomic<unsigned> attr_done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned bit = 1u << (dev & 31);
+    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      attr_done.fetch_or(bit, std::memory_order_release);
+    }
+  }
   kern<<<(unsigned)blocks, G::NT, G::SMEM_BYTES, st>>>(prm);
   count_launch(OP == LAP ? "fused_laplacian3d" : OP == DIV ? "fused_divergence3d" : OP == GRAD ? "fused_gradient3d" : "fused_curl3d");
   FDX_LAUNCH_CHECK();

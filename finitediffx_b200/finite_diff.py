@@ -261,6 +261,28 @@ def _run(x_fields: torch.Tensor, terms, n_out: int) -> torch.Tensor:
     return _StencilOp.apply(x_fields, terms, n_out)
 
 
+_terms_memo: dict = {}
+_plan_mod._dependent_caches.append(_terms_memo.clear)
+
+
+def _memo_terms(op: str, nd: int, accuracy, step_size, method, build):
+    """Term lists are pure functions of (operator, rank, accuracy, step_size, method): repeated calls
+    with plain Python scalars / tuples (the common case) skip validation and construction."""
+    def plain(v):
+        return type(v) in (int, float) or (type(v) is tuple and all(type(e) in (int, float) for e in v))
+
+    if not (plain(accuracy) and plain(step_size) and type(method) is str):
+        return build()  # arrays / tensors: their values may change, build every time
+    key = (op, nd, accuracy, step_size, method)
+    hit = _terms_memo.get(key)
+    if hit is None:
+        hit = tuple(build())
+        if len(_terms_memo) > 256:
+            _terms_memo.clear()
+        _terms_memo[key] = hit
+    return hit
+
+
 # --------------------------------------------------------------------------------- operators
 def difference(
     array,
@@ -305,10 +327,13 @@ def gradient(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
     if streamed is not None:
         return streamed
     x, restore = _to_device(array)
-    accuracy = _check_and_return(accuracy, x.ndim, "accuracy")
-    step_size = _check_and_return(step_size, x.ndim, "step_size")
-    terms = [Term(k, 0, k, 1, int(a), method, _alpha(h, 1)) for k, (a, h) in enumerate(zip(accuracy, step_size))]
-    return restore(_run(x.unsqueeze(0), terms, x.ndim))
+
+    def build():
+        acc = _check_and_return(accuracy, x.ndim, "accuracy")
+        steps = _check_and_return(step_size, x.ndim, "step_size")
+        return [Term(k, 0, k, 1, int(a), method, _alpha(h, 1)) for k, (a, h) in enumerate(zip(acc, steps))]
+
+    return restore(_run(x.unsqueeze(0), _memo_terms("gradient", x.ndim, accuracy, step_size, method, build), x.ndim))
 
 
 def jacobian(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
@@ -341,10 +366,14 @@ def divergence(array, *, accuracy=1, step_size=1, keepdims: bool = True, method:
         return streamed[None] if keepdims else streamed
     x, restore = _to_device(array)
     nd = x.ndim - 1
-    accuracy = _check_and_return(accuracy, nd, "accuracy")
-    step_size = _check_and_return(step_size, nd, "step_size")
-    # zip() in the reference stops at ndim-1 axes: extra leading components are ignored
-    terms = [Term(0, k, k, 1, int(a), method, _alpha(h, 1)) for k, (a, h) in enumerate(zip(accuracy, step_size))]
+
+    def build():
+        acc = _check_and_return(accuracy, nd, "accuracy")
+        steps = _check_and_return(step_size, nd, "step_size")
+        # zip() in the reference stops at ndim-1 axes: extra leading components are ignored
+        return [Term(0, k, k, 1, int(a), method, _alpha(h, 1)) for k, (a, h) in enumerate(zip(acc, steps))]
+
+    terms = _memo_terms("divergence", nd, accuracy, step_size, method, build)
     if x.shape[0] < nd:
         raise IndexError(f"index {x.shape[0]} is out of bounds for axis 0 with size {x.shape[0]}")
     out = _run(x, terms, 1)
@@ -383,10 +412,13 @@ def laplacian(array, *, accuracy=1, step_size=1, method: MethodKind = "central")
     if streamed is not None:
         return streamed
     x, restore = _to_device(array)
-    accuracy = _check_and_return(accuracy, x.ndim, "accuracy")
-    step_size = _check_and_return(step_size, x.ndim, "step_size")
-    terms = [Term(0, 0, k, 2, int(a), method, _alpha(h, 2)) for k, (a, h) in enumerate(zip(accuracy, step_size))]
-    return restore(_run(x.unsqueeze(0), terms, 1).squeeze(0))
+
+    def build():
+        acc = _check_and_return(accuracy, x.ndim, "accuracy")
+        steps = _check_and_return(step_size, x.ndim, "step_size")
+        return [Term(0, 0, k, 2, int(a), method, _alpha(h, 2)) for k, (a, h) in enumerate(zip(acc, steps))]
+
+    return restore(_run(x.unsqueeze(0), _memo_terms("laplacian", x.ndim, accuracy, step_size, method, build), 1).squeeze(0))
 
 
 def curl(array, *, accuracy=1, step_size=1, method: MethodKind = "central", keepdims: bool = True):
