@@ -333,7 +333,12 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   b /= prm.tiles_x;
   const int tile_y = b % prm.tiles_y;
   const int cslot = b / prm.tiles_y;  // chunks are listed in launch order (see launch_cfg)
-  const int x0 = tile_x * G::TX, y0 = tile_y * G::TY;
+  // the last tile of a row is shifted left so that it is a full tile ending at column n2 (it then holds
+  // the whole right band and all of its taps however n2 relates to TX); a tile writes only the columns
+  // before the next tile's origin, so no output is written twice
+  const int x_shift = max(0, n2 - G::TX);
+  const int x0 = min(tile_x * G::TX, x_shift), y0 = tile_y * G::TY;
+  const int x_hi = tile_x + 1 < prm.tiles_x ? min((tile_x + 1) * G::TX, x_shift) : n2;
   const int zs = prm.cut_z[cslot];
   const int ze = zs + prm.cut_n[cslot];
   const int zin0 = max(zs - P, prm.z_lo);
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // row j of this thread lies inside the grid: bit j (opaque, so that it stays one register)
   uint32_t rmask = 0;
 #pragma unroll
-  for (int j = 0; j < RY; ++j) rmask |= ((xg < n2) && (yg + j < n1)) ? (1u << j) : 0u;
+  for (int j = 0; j < RY; ++j) rmask |= ((xg < x_hi) && (yg + j < n1)) ? (1u << j) : 0u;
   asm volatile("" : "+r"(rmask));
   auto rok = [&](int j) { return (rmask >> j) & 1u; };
 
@@ -968,7 +973,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
           ok = false;
       }
     // the last tile must hold the three vectors that end at column n2 - 1
-    const int xl_last = ((n2 + G::TX - 1) / G::TX - 1) * G::TX;
+    const int xl_last = n2 > G::TX ? n2 - G::TX : 0;  // origin of the (shifted) last tile
     if (n2 - xl_last < 3 * XV - G::HX) ok = false;
     if (((n2 - xl_last) / XV - 1) % CFG::LX < CFG::RY - 1) ok = false;  // the helper lanes sit in the owner's warp
     if (env_int("FDX_XBAND_SLOW", 0)) ok = false;
@@ -987,7 +992,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     // the x bands are evaluated from the first / last tile in shared memory: those tiles must hold
     // every band output of their side and all of its taps (otherwise: composition fallback)
     const fdx_plan_s* px = plans[2];
-    const int xl = (prm.tiles_x - 1) * G::TX;
+    const int xl = n2 > G::TX ? n2 - G::TX : 0;  // origin of the (shifted) last tile
     if (px->nl > G::TX || px->wl > G::TX + G::HX || n2 - xl < px->nr || xl > n2 - px->wr + G::HX) return FDX_EUNSUPPORTED;
     if (px->nl * px->wl + px->nr * px->wr > kXTabMax) return FDX_EUNSUPPORTED;
   }

@@ -357,3 +357,77 @@ def test_full_size_properties_512cubed_fp32():
         scale = sum(O.conditioning_scale(brick, axis=k, accuracy=4, derivative=2, method="central", step_size=h) for k in range(3))
         err = np.max(np.abs(got - refb[core]) / scale[core])
         assert err <= 1e-5, (sl, err)
+
+
+# ------------------------------------------------------------- fused-kernel code paths (round 1)
+def _env(**kw):
+    import contextlib
+    import os
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kw}
+        os.environ.update({k: str(v) for k, v in kw.items()})
+        try:
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    return cm()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_fused_result_does_not_depend_on_the_z_chunking(dtype):
+    """Graded / uniform / explicit z chunks, tiny chunks included, give bit-identical outputs: every
+    output plane receives the same taps in the same order whatever chunk it falls in."""
+    x = torch.randn(150, 40, 72, device="cuda", dtype=dtype)
+    f = torch.randn(3, 150, 40, 72, device="cuda", dtype=dtype)
+    calls = {
+        "laplacian": lambda: fdx.laplacian(x, accuracy=4, step_size=0.1),
+        "gradient": lambda: fdx.gradient(x, accuracy=4, step_size=0.1),
+        "divergence": lambda: fdx.divergence(f, accuracy=6, step_size=0.1, keepdims=False),
+        "curl": lambda: fdx.curl(f, accuracy=2, step_size=0.1),
+    }
+    for name, call in calls.items():
+        ref = call()
+        assert _cabi.last_kernel().startswith("fused_"), (name, _cabi.last_kernel())
+        for env in (dict(FDX_FUSED_CHUNK=4), dict(FDX_FUSED_CHUNK=7), dict(FDX_FUSED_CHUNK=64), dict(FDX_FUSED_CHUNK=300),
+                    dict(FDX_FUSED_CHUNK=48, FDX_FUSED_CHUNK_SHORT=8), dict(FDX_FUSED_CUTS="5,9,40,3,60")):
+            with _env(**env):
+                out = call()
+            assert _cabi.last_kernel().startswith("fused_"), (name, env)
+            assert torch.equal(out, ref), (name, env, (out - ref).abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_x_band_paths_and_awkward_tiles(dtype):
+    """x bands: the register fast path, the warp-cooperative path (forced with FDX_XBAND_SLOW, and taken
+    on its own by wide adjoint bands) and shapes whose last tile is narrow or partial, against the oracle."""
+    rng = np.random.default_rng(7)
+    for shape in ((20, 18, 64), (20, 33, 68), (17, 16, 132), (24, 40, 12), (12, 50, 200)):
+        x = rng.standard_normal(shape).astype(dtype)
+        f = rng.standard_normal((3,) + shape).astype(dtype)
+        for acc in (2, 4, 6):
+            for slow in (0, 1):
+                with _env(FDX_XBAND_SLOW=slow):
+                    for op, arr, kw in (("laplacian", x, dict(accuracy=acc, step_size=0.3)), ("divergence", f, dict(accuracy=acc, step_size=0.3, keepdims=False)),
+                                        ("gradient", x, dict(accuracy=acc, step_size=0.3)), ("curl", f, dict(accuracy=acc, step_size=0.3))):
+                        out = _call(op, arr, **kw)
+                        assert _cabi.last_kernel().startswith("fused_"), (op, shape, acc, _cabi.last_kernel())
+                        err = parity_error(op, arr, kw, out, getattr(O, op)(arr, **kw))
+                        assert err <= TOL[np.dtype(dtype)], (op, shape, acc, slow, err)
+
+
+def test_tiny_and_thin_grids_take_the_fused_path():
+    """Grids of a few tiles (very short z chunks) and slabs thinner than a tile."""
+    rng = np.random.default_rng(8)
+    for shape in ((8, 8, 8), (9, 300, 16), (300, 9, 16), (16, 9, 300), (100, 100, 100)):
+        x = rng.standard_normal(shape).astype(np.float32)
+        kw = dict(accuracy=2, step_size=0.5)
+        out = _call("laplacian", x, **kw)
+        assert _cabi.last_kernel().startswith("fused_"), (shape, _cabi.last_kernel())
+        assert parity_error("laplacian", x, kw, out, O.laplacian(x, **kw)) <= 1e-5, shape
