@@ -36,6 +36,9 @@ WORKLOADS = {
     "curl_512_f32_a4": dict(op="curl", n=512, dtype="f32", accuracy=4, fields_in=3, fields_out=3),
     "laplacian_512_f64_a8": dict(op="laplacian", n=512, dtype="f64", accuracy=8, fields_in=1, fields_out=1),
     "laplacian_1024_f32_a4": dict(op="laplacian", n=1024, dtype="f32", accuracy=4, fields_in=1, fields_out=1),
+    # BASELINE config 5: a FIXED 2048^3 fp64 grid, accuracy 8, slab-decomposed over the N ranks (strong scaling;
+    # 137 GB of HBM at N=1, 17 GB per rank at N=8)
+    "laplacian_2048_f64_a8_strong": dict(op="laplacian", n=2048, dtype="f64", accuracy=8, fields_in=1, fields_out=1, strong=True),
 }
 HEADLINE = "laplacian_512_f32_a4"
 
@@ -300,7 +303,19 @@ def run_ours(args):
     _cabi.load()
 
     barrier = (lambda: dist.barrier()) if dist else None
-    if world == 1:
+    strong = bool(w.get("strong"))
+    if strong:
+        from finitediffx_b200 import distributed as fd
+
+        if n % world:
+            raise SystemExit(f"{args.workload}: {n} planes do not split over {world} ranks")
+        pts_per_gpu = n**3 // world
+        slab = fd.Slab(global_n0=n, rank=rank, world=world, group=dist.group.WORLD if dist else None)
+        op = fd.SlabOperator(slab, w["op"], spatial=(n, n, n), dtype=torch.float32 if w["dtype"] == "f32" else torch.float64, accuracy=w["accuracy"], step_size=1.0 / (n - 1), device=dev, n_buffers=1)
+        op.fill_random(0, seed=100 * rank)
+        inputs = [0]
+        fn = lambda b: op.step(b)
+    elif world == 1:
         # rotate over 3 input buffers so nothing stays L2-resident between steps (inputs >> L2)
         inputs = [_make_input(w, dev, seed=s) for s in range(3)]
         fn = lambda x: _call(fdx, w, x)
@@ -333,7 +348,7 @@ def run_ours(args):
 
     # ---- end-to-end through the public API with HOST buffers (H2D + kernel + D2H every step)
     e2e = None
-    if world == 1:
+    if world == 1 and not strong:
         hx = [torch.empty(inputs[0].shape, dtype=inputs[0].dtype, pin_memory=True).copy_(inputs[i]) for i in range(2)]
         e_steps = max(3, min(args.steps, 10))
         r = None
@@ -355,7 +370,7 @@ def run_ours(args):
             "api": f"finitediffx_b200.{w['op']}(pinned host tensor) -> host tensor",
         }
     else:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "slab data is device-resident at N>1; e2e is measured at N=1"}
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "slab data is device-resident at N>1 and for the strong-scaling workload; e2e is measured at N=1 on the headline workload"}
 
     if rank != 0:
         if dist:
@@ -381,19 +396,19 @@ def run_ours(args):
         "warmup": args.warmup,
         "ms_per_step": ms,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None,
         "dtype": w["dtype"],
         "data": "synthetic",
         "config": {
             "workload": args.workload,
-            "grid": [n * world, n, n],
-            "grid_per_gpu": [n, n, n],
+            "grid": [n, n, n] if strong else [n * world, n, n],
+            "grid_per_gpu": [n // world, n, n] if strong else [n, n, n],
             "accuracy": w["accuracy"],
             "method": "central",
             "step_size": f"1/{n - 1}",
             "decomposition": "single GPU" if world == 1 else f"slab along axis 0, {world} ranks, NCCL halo exchange",
-            "l2": "3 rotating inputs, each larger than L2 (126 MB); outputs freshly written",
+            "l2": "one input slab per rank, far larger than L2 (126 MB)" if strong else "3 rotating inputs, each larger than L2 (126 MB); outputs freshly written",
         },
         "clocks": sampler.summary() if sampler else None,
         "e2e": e2e,
@@ -411,9 +426,9 @@ def run_ours(args):
             "traffic": traffic,
         },
     }
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not strong:
         line["cpu_baseline"] = _cpu_baseline(w)
-    if world == 1 and args.extras:
+    if world == 1 and args.extras and not strong:
         extras = {}
         for name in ("divergence_512_f32_a4", "gradient_512_f32_a4", "curl_512_f32_a4", "laplacian_512_f64_a8"):
             if name == args.workload:

@@ -119,7 +119,9 @@ class SlabOperator:
     def fill_random(self, b: int, seed: int) -> None:
         g = torch.Generator(device=self.device).manual_seed(seed)
         for f in range(len(self.inputs[b])):
-            self.owned_view(b, f).copy_(torch.randn(self.owned_view(b, f).shape, generator=g, device=self.device, dtype=self.dtype))
+            v = self.owned_view(b, f)
+            for z in range(0, v.shape[0], 64):  # in pieces: a 2048^3 slab must not need a second copy of itself
+                v[z : z + 64].normal_(generator=g)
 
     # -- one operator application ------------------------------------------------------------
     def step(self, b: int = 0) -> List[torch.Tensor]:
