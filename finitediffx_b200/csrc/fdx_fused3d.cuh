@@ -24,6 +24,7 @@
 // back -- inside the library, still on the GPU -- to the composition of axis kernels.
 #include <cuda.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
@@ -106,6 +107,10 @@ struct FusedParams {
   // v - (V - nr) that sits t columns before the row's own column
   static constexpr int kXV = 16 / (int)sizeof(T), kXT = 2 * kXV + 1;
   int xfast, xnt_l, xnt_r;
+  int plain_ok;  // interior CTAs may take the specialised (flag-free) march
+  int rim_first;  // launch order inside a chunk layer: rim tiles first (FDX_FUSED_RIMFIRST=0 switches it off)
+  int dbg;       // experiments only (FDX_FUSED_DBG): 2 no x-band work, 16 every tile takes the interior copy (both: wrong results at the edges)
+  int xdirect;   // ... and so may the tiles with x-band columns (the owner's window holds all band taps)
   T xcl[kXT][kXV], xcr[kXT][kXV];
   short2 rng[kRowsMax];  // [first, last+1) nonzero band column of every band row
   T tab[kTabMax];
@@ -299,6 +304,12 @@ struct InPlane {
   __host__ __device__ static constexpr int xfield(int q) { return OP == DIV ? 2 : (OP == CURL ? (q == 0 ? 1 : 0) : 0); }
 };
 
+// output o of OP is written at plane zc - lag: P for the outputs that leave the z queue, 0 for in-plane ones
+template <Op OP, int P>
+__host__ __device__ constexpr int out_lag(int o) {
+  return (OP == LAP || OP == DIV) ? P : (OP == GRAD ? (o == 0 ? P : 0) : (o == 0 ? 0 : P));
+}
+
 template <Op OP, typename T, int P, typename CFG>
 __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     fused3d_kernel(const __grid_constant__ FusedParams<T> prm) {
@@ -328,11 +339,26 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   const int n0 = prm.ax[0].n, n1 = prm.ax[1].n, n2 = prm.ax[2].n;
 
   // ---- work item: (tile, chunk); tile fastest so that concurrently resident CTAs share halos in L2
-  int b = blockIdx.x;
-  const int tile_x = b % prm.tiles_x;
-  b /= prm.tiles_x;
-  const int tile_y = b % prm.tiles_y;
-  const int cslot = b / prm.tiles_y;  // chunks are listed in launch order (see launch_cfg)
+  // Within a chunk layer the tiles on the rim of the (y,x) plane come first: they carry the band work and are
+  // the slowest CTAs, so they must not be the last ones of the launch.
+  int tile_x, tile_y, cslot;
+  {
+    const int txn = prm.tiles_x, tyn = prm.tiles_y, tiles = txn * tyn;
+    const int b = blockIdx.x;
+    cslot = b / tiles;  // chunks are listed in launch order (see launch_cfg)
+    int r = b - cslot * tiles;
+    if (txn < 3 || tyn < 3 || prm.rim_first == 0) {
+      tile_x = r % txn, tile_y = r / txn;
+    } else if (r < 2 * txn) {
+      tile_y = r < txn ? 0 : tyn - 1, tile_x = r < txn ? r : r - txn;
+    } else if (r < 2 * txn + 2 * (tyn - 2)) {
+      r -= 2 * txn;
+      tile_y = 1 + (r >> 1), tile_x = (r & 1) ? txn - 1 : 0;
+    } else {
+      r -= 2 * txn + 2 * (tyn - 2);
+      tile_y = 1 + r / (txn - 2), tile_x = 1 + r % (txn - 2);
+    }
+  }
   // the last tile of a row is shifted left so that it is a full tile ending at column n2 (it then holds
   // the whole right band and all of its taps however n2 relates to TX); a tile writes only the columns
   // before the next tile's origin, so no output is written twice
@@ -418,7 +444,10 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   uint32_t tb[Tr::NIN];
 #pragma unroll
   for (int f = 0; f < Tr::NIN; ++f)
+  {
     tb[f] = ring + G::field_off(f) + (uint32_t)sizeof(T) * ((ty * RY) * G::box_x(f) + G::xoff(f) + tx * V);
+    asm volatile("" : "+r"(tb[f]));  // opaque: one register instead of a re-derivation per plane
+  }
   // output row bases: address of element (plane 0, row yg + j, column xg) of every output, held in
   // registers (opaque) so that a store costs one IMAD.WIDE for its address
   uint64_t ob[Tr::NOUT][RY];
@@ -445,8 +474,14 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     }
   };
   // D_x for one row: `row` is the shared address of this thread's vector inside a tile row with x halos
-  auto dx_main = [&](uint32_t row, const VT& centre) {
-    T w[(2 * HXV + 1) * V];
+  // With `xb` (a constant at every call site; specialised march of a tile with x-band columns) the thread
+  // that owns the band columns of a side replaces them: band row v is the dot product of its taps
+  // xcl[t][v] / xcr[t][v] (prm.xfast layout) with the window it already holds, taps in ascending column
+  // order like the reference's sum.  The host guarantees that the window reaches far enough (prm.xdirect).
+  const bool own_l = xedge_l && tx == 0 && !(prm.dbg & 2), own_r = xedge_r && tx == (n2 - V - x0) / V && !(prm.dbg & 2);
+  auto dx_main = [&](uint32_t row, const VT& centre, bool xb) {
+    constexpr int W = (2 * HXV + 1) * V;
+    T w[W];
 #pragma unroll
     for (int h = 0; h < HXV; ++h) {
       const VT l = lds_vec<T, V>(row - (uint32_t)((HXV - h) * V * sizeof(T)));
@@ -466,6 +501,41 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 #pragma unroll
       for (int k = 1; k < WZ; ++k) s = fma(A2.c[k], w[HX + v - P + k], s);
       r.v[v] = s;
+    }
+    if (xb) {
+      constexpr int XT = FusedParams<T>::kXT;
+      if (own_l) {
+        T val[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) val[v] = 0;
+#pragma unroll
+        for (int t = 0; t < XT; ++t) {
+          if (t < prm.xnt_l) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+              if (HX + v + t < W) val[v] = fma(prm.xcl[t][v], w[HX + v + t], val[v]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (v < A2.nl) r.v[v] = val[v] * A2.alpha;
+      }
+      if (own_r) {
+        T val[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) val[v] = 0;
+#pragma unroll
+        for (int t = XT - 1; t >= 0; --t) {
+          if (t < prm.xnt_r) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+              if (HX + v - t >= 0) val[v] = fma(prm.xcr[t][v], w[HX + v - t], val[v]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (v >= V - A2.nr) r.v[v] = val[v] * A2.alpha;
+      }
     }
     return r;
   };
@@ -674,6 +744,214 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   int stage = 0;           // it % STAGES
   uint32_t soff = 0;       // stage * STAGE_BYTES
   uint32_t full_parity = 0;
+
+  // ---------------- pieces of one march step (shared by the generic and the specialised loop)
+  // hot: loads of plane zc and its in-plane taps
+  auto hot_inplane = [&](VT (&zv)[Tr::NACC][RY], VT (&ya)[NY][RY], VT (&xa)[NX][RY], bool xb) {
+    if constexpr (OP == LAP || OP == GRAD) {
+#pragma unroll
+      for (int i = 0; i < RY + 2 * P; ++i) {
+        const uint32_t row = tb[0] + soff + (uint32_t)(i * G::box_x(0) * sizeof(T));
+        const VT ci = lds_vec<T, V>(row);
+        dy_feed(ya[0], ci, i);
+        if (i >= P && i < P + RY) {
+          zv[0][i - P] = ci;
+          xa[0][i - P] = dx_main(row, ci, xb);
+        }
+      }
+    } else if constexpr (OP == DIV) {
+#pragma unroll
+      for (int j = 0; j < RY; ++j) zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)(j * G::box_x(0) * sizeof(T)));
+#pragma unroll
+      for (int i = 0; i < RY + 2 * P; ++i)
+        dy_feed(ya[0], lds_vec<T, V>(tb[1] + soff + (uint32_t)(i * G::box_x(1) * sizeof(T))), i);
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        const uint32_t row = tb[2] + soff + (uint32_t)(j * G::box_x(2) * sizeof(T));
+        xa[0][j] = dx_main(row, lds_vec<T, V>(row), xb);
+      }
+    } else {  // CURL
+#pragma unroll
+      for (int i = 0; i < RY + 2 * P; ++i) {
+        const VT ci = lds_vec<T, V>(tb[2] + soff + (uint32_t)(i * G::box_x(2) * sizeof(T)));
+        dy_feed(ya[0], ci, i);                        // D1 x2
+        if (i >= P && i < P + RY) zv[0][i - P] = ci;  // x2 -> -D0 x2 into out_1
+      }
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        const uint32_t row = tb[1] + soff + (uint32_t)(j * G::box_x(1) * sizeof(T));
+        zv[1][j] = lds_vec<T, V>(row);      // x1 -> +D0 x1 into out_2
+        xa[0][j] = dx_main(row, zv[1][j], xb);  // D2 x1
+      }
+#pragma unroll
+      for (int i = 0; i < RY + 2 * P; ++i) {
+        const uint32_t row = tb[0] + soff + (uint32_t)(i * G::box_x(0) * sizeof(T));
+        const VT ci = lds_vec<T, V>(row);
+        dy_feed(ya[1], ci, i);                                       // D1 x0
+        if (i >= P && i < P + RY) xa[1][i - P] = dx_main(row, ci, xb);  // D2 x0
+      }
+    }
+  };
+  // warm-up / cool-down plane: only the values that enter the z taps
+  auto zonly_loads = [&](VT (&zv)[Tr::NACC][RY]) {
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      if constexpr (OP == LAP || OP == GRAD) {
+        zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)((P + j) * G::box_x(0) * sizeof(T)));
+      } else if constexpr (OP == DIV) {
+        zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)(j * G::box_x(0) * sizeof(T)));
+      } else {
+        zv[0][j] = lds_vec<T, V>(tb[2] + soff + (uint32_t)((P + j) * G::box_x(2) * sizeof(T)));
+        zv[1][j] = lds_vec<T, V>(tb[1] + soff + (uint32_t)(j * G::box_x(1) * sizeof(T)));
+      }
+    }
+  };
+  // in-plane results: straight out (ip: GRAD out_1, out_2; CURL out_0 -- stored by the caller at plane zc), or
+  // towards output plane zc of the queue (tin)
+  constexpr int NIP = OP == GRAD ? 2 : (OP == CURL ? 1 : 0);
+  auto combine = [&](VT (&ya)[NY][RY], VT (&xa)[NX][RY], VT (&tin)[Tr::NACC][RY], VT (&ip)[NIP + 1][RY]) {
+#pragma unroll
+    for (int j = 0; j < RY; ++j) {
+      if constexpr (OP == LAP || OP == DIV) {
+        tin[0][j] = ya[0][j];
+        add_vec(tin[0][j], xa[0][j]);
+      } else if constexpr (OP == GRAD) {
+        ip[0][j] = ya[0][j];
+        ip[1][j] = xa[0][j];
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          ip[0][j].v[v] = ya[0][j].v[v] - xa[0][j].v[v];
+          tin[0][j].v[v] = xa[1][j].v[v];
+          tin[1][j].v[v] = -ya[1][j].v[v];
+        }
+      }
+    }
+  };
+  // this warp no longer reads the stage: release it (one arrive per warp), move to the next stage
+  auto release = [&]() {
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(bar_empty + 8u * stage);
+    if (++stage == STAGES) {
+      stage = 0, soff = 0, full_parity ^= 1u;
+    } else {
+      soff += G::STAGE_BYTES;
+    }
+  };
+  // z taps: complete the oldest queue entry (eo: output plane zc - P, stored by the caller), shift the others
+  auto ztaps = [&](VT (&zv)[Tr::NACC][RY], bool emit, VT (&eo)[Tr::NACC][RY]) {
+#pragma unroll
+    for (int a = 0; a < Tr::NACC; ++a) {
+      const T sgn = (OP == CURL && a == 0) ? (T)-1 : (T)1;
+      if (emit) {
+#pragma unroll
+        for (int j = 0; j < RY; ++j) fma_to(eo[a][j], sgn * A0.c[2 * P], zv[a][j], q[a][2 * P - 1][j]);
+      }
+#pragma unroll
+      for (int i = 2 * P - 1; i >= 1; --i)
+#pragma unroll
+        for (int j = 0; j < RY; ++j) fma_to(q[a][i][j], sgn * A0.c[i], zv[a][j], q[a][i - 1][j]);
+#pragma unroll
+      for (int j = 0; j < RY; ++j) fma_vec<true>(q[a][0][j], sgn * A0.c[0], zv[a][j]);
+    }
+  };
+  // in-plane part of plane zc joins its output (which has just received tap P)
+  auto join = [&](VT (&tin)[Tr::NACC][RY]) {
+    if constexpr (OP != GRAD) {
+#pragma unroll
+      for (int a = 0; a < Tr::NACC; ++a)
+#pragma unroll
+        for (int j = 0; j < RY; ++j) add_vec(q[a][P][j], tin[a][j]);
+    }
+  };
+
+  // ---- specialised march: a CTA with a full tile whose chunk stays clear of the z bands knows its whole
+  // schedule -- P warm-up planes, P planes that do not emit yet, the steady state, P cool-down planes --
+  // so the loop carries no per-plane flag bytes, no row masks and running output pointers.  Three
+  // copies: interior tiles and tiles with band rows / columns (partial tiles and the chunks that hold
+  // z-band planes take the generic march below).
+  const int nout = ze - zs;
+  const bool fast_ok = prm.plain_ok && (x0 + G::TX <= x_hi) && (y0 + G::TY <= n1) && zs >= A0.nl && ze <= n0 - A0.nr &&
+                       n_planes == nout + 2 * P && (!(xedge_l || xedge_r) || prm.xdirect || (prm.dbg & 16));
+  if (fast_ok) {
+    uint64_t oz[Tr::NOUT][RY];
+#pragma unroll
+    for (int o = 0; o < Tr::NOUT; ++o)
+#pragma unroll
+      for (int j = 0; j < RY; ++j) oz[o][j] = ob[o][j] + (uint64_t)((int64_t)(zin0 - out_lag<OP, P>(o)) * (int64_t)plane_b);
+    auto st = [&](int o, int j, const VT& val) { stg_vec<T, V>(oz[o][j], val); };
+    int it = 0;
+    // be: the copy for tiles with band rows / columns (constant at every call site).  phase: 0 = inr / emit
+    // from the plane counter (one loop); 1 .. 4 = constants (warm-up, no emit yet, steady state, cool-down:
+    // four loops, no flags at all)
+    auto step = [&](bool be, int phase) {
+      const bool xe = be, ye = be;
+      const bool inr = phase == 0 ? (it >= P && it < P + nout) : (phase == 2 || phase == 3);  // also an output plane of ours
+      const bool emit = phase == 0 ? (it >= 2 * P) : (phase >= 3);  // output plane zc - P is complete after this step
+      if (tid == 0 && it + LOOK < n_planes) issue(it + LOOK);
+      mbar_wait_a(bar_full + 8u * stage, full_parity);
+      VT zv[Tr::NACC][RY], tin[Tr::NACC][RY], eo[Tr::NACC][RY];
+      if (inr) {
+        VT ya[NY][RY], xa[NX][RY], ip[NIP + 1][RY];
+        hot_inplane(zv, ya, xa, xe);
+        if (ye) {
+          if (yband) {
+            const int64_t zofs = (int64_t)(zin0 + it) * plane;
+#pragma unroll
+            for (int qq = 0; qq < NY; ++qq) {
+              const int f = IP::yfield(qq);
+              const T* tile = reinterpret_cast<const T*>(smem_raw + (ring - smem0) + soff + G::field_off(f));
+#pragma unroll
+              for (int j = 0; j < RY; ++j)
+                if (is_yband(j))
+                  ya[qq][j] = band_y(tile + G::xoff(f) + tx * V, G::box_x(f), G::box_y(f), prm.in[f] + zofs + xg, yg + j);
+            }
+          }
+        }
+        combine(ya, xa, tin, ip);
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+          if constexpr (OP == GRAD) st(1, j, ip[0][j]), st(2, j, ip[1][j]);
+          if constexpr (OP == CURL) st(0, j, ip[0][j]);
+        }
+      } else {
+        zonly_loads(zv);
+      }
+      release();
+      ztaps(zv, emit, eo);
+      if (emit) {
+#pragma unroll
+        for (int a = 0; a < Tr::NACC; ++a)
+#pragma unroll
+          for (int j = 0; j < RY; ++j) st(OP == CURL ? a + 1 : 0, j, eo[a][j]);
+      }
+      if (inr) join(tin);
+      ++it;
+#pragma unroll
+      for (int o = 0; o < Tr::NOUT; ++o)
+#pragma unroll
+        for (int j = 0; j < RY; ++j) oz[o][j] += (uint64_t)plane_b;
+    };
+    if (edge && !(prm.dbg & 16)) {
+#pragma unroll 1
+      for (int k = n_planes; k > 0; --k) step(true, 0);
+    } else if (nout >= P) {
+#pragma unroll 1
+      for (int k = 0; k < P; ++k) step(false, 1);
+#pragma unroll 1
+      for (int k = 0; k < P; ++k) step(false, 2);
+#pragma unroll 1
+      for (int k = nout - P; k > 0; --k) step(false, 3);
+#pragma unroll 1
+      for (int k = 0; k < P; ++k) step(false, 4);
+    } else {
+#pragma unroll 1
+      for (int k = n_planes; k > 0; --k) step(true, 0);
+    }
+    return;
+  }
+
+  // ---- generic march: per-plane flags, band sections
   int zc = zin0;
   auto lds_flag = [&](int i) {
     uint32_t f;
@@ -695,50 +973,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     VT tin[Tr::NACC][RY];  // in-plane contribution to output plane zc of each accumulator set
     if (inr) {
       VT ya[NY][RY], xa[NX][RY];  // raw in-plane derivatives of plane zc
-      // ---------------- hot: loads and in-plane taps
-      if constexpr (OP == LAP || OP == GRAD) {
-#pragma unroll
-        for (int i = 0; i < RY + 2 * P; ++i) {
-          const uint32_t row = tb[0] + soff + (uint32_t)(i * G::box_x(0) * sizeof(T));
-          const VT ci = lds_vec<T, V>(row);
-          dy_feed(ya[0], ci, i);
-          if (i >= P && i < P + RY) {
-            zv[0][i - P] = ci;
-            xa[0][i - P] = dx_main(row, ci);
-          }
-        }
-      } else if constexpr (OP == DIV) {
-#pragma unroll
-        for (int j = 0; j < RY; ++j) zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)(j * G::box_x(0) * sizeof(T)));
-#pragma unroll
-        for (int i = 0; i < RY + 2 * P; ++i)
-          dy_feed(ya[0], lds_vec<T, V>(tb[1] + soff + (uint32_t)(i * G::box_x(1) * sizeof(T))), i);
-#pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          const uint32_t row = tb[2] + soff + (uint32_t)(j * G::box_x(2) * sizeof(T));
-          xa[0][j] = dx_main(row, lds_vec<T, V>(row));
-        }
-      } else {  // CURL
-#pragma unroll
-        for (int i = 0; i < RY + 2 * P; ++i) {
-          const VT ci = lds_vec<T, V>(tb[2] + soff + (uint32_t)(i * G::box_x(2) * sizeof(T)));
-          dy_feed(ya[0], ci, i);                        // D1 x2
-          if (i >= P && i < P + RY) zv[0][i - P] = ci;  // x2 -> -D0 x2 into out_1
-        }
-#pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          const uint32_t row = tb[1] + soff + (uint32_t)(j * G::box_x(1) * sizeof(T));
-          zv[1][j] = lds_vec<T, V>(row);      // x1 -> +D0 x1 into out_2
-          xa[0][j] = dx_main(row, zv[1][j]);  // D2 x1
-        }
-#pragma unroll
-        for (int i = 0; i < RY + 2 * P; ++i) {
-          const uint32_t row = tb[0] + soff + (uint32_t)(i * G::box_x(0) * sizeof(T));
-          const VT ci = lds_vec<T, V>(row);
-          dy_feed(ya[1], ci, i);                                       // D1 x0
-          if (i >= P && i < P + RY) xa[1][i - P] = dx_main(row, ci);  // D2 x0
-        }
-      }
+      hot_inplane(zv, ya, xa, false);
       // ---------------- cold: rows / columns next to a physical boundary of the grid
       if (slow && edge) {
         const int64_t zofs = (int64_t)zc * plane;
@@ -765,25 +1000,12 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
           }
         }
       }
-      // ---------------- in-plane results: straight out, or towards output plane zc of the queue
+      VT ip[NIP + 1][RY];
+      combine(ya, xa, tin, ip);
 #pragma unroll
       for (int j = 0; j < RY; ++j) {
-        if constexpr (OP == LAP || OP == DIV) {
-          tin[0][j] = ya[0][j];
-          add_vec(tin[0][j], xa[0][j]);
-        } else if constexpr (OP == GRAD) {
-          store(1, zc, j, ya[0][j]);
-          store(2, zc, j, xa[0][j]);
-        } else {
-          VT o0;
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            o0.v[v] = ya[0][j].v[v] - xa[0][j].v[v];
-            tin[0][j].v[v] = xa[1][j].v[v];
-            tin[1][j].v[v] = -ya[1][j].v[v];
-          }
-          store(0, zc, j, o0);
-        }
+        if constexpr (OP == GRAD) store(1, zc, j, ip[0][j]), store(2, zc, j, ip[1][j]);
+        if constexpr (OP == CURL) store(0, zc, j, ip[0][j]);
       }
       if (zb) {  // cold: plane next to a physical z boundary, one-sided taps gathered directly
 #pragma unroll
@@ -807,55 +1029,19 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
           }
         }
       }
-    } else {  // warm-up / cool-down plane: only the z taps are wanted
-#pragma unroll
-      for (int j = 0; j < RY; ++j) {
-        if constexpr (OP == LAP || OP == GRAD) {
-          zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)((P + j) * G::box_x(0) * sizeof(T)));
-        } else if constexpr (OP == DIV) {
-          zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)(j * G::box_x(0) * sizeof(T)));
-        } else {
-          zv[0][j] = lds_vec<T, V>(tb[2] + soff + (uint32_t)((P + j) * G::box_x(2) * sizeof(T)));
-          zv[1][j] = lds_vec<T, V>(tb[1] + soff + (uint32_t)(j * G::box_x(1) * sizeof(T)));
-        }
-      }
-    }
-    // this warp no longer reads the stage: release it (one arrive per warp)
-    __syncwarp();
-    if (lane == 0) mbar_arrive_a(bar_empty + 8u * stage);
-    if (++stage == STAGES) {
-      stage = 0, soff = 0, full_parity ^= 1u;
     } else {
-      soff += G::STAGE_BYTES;
+      zonly_loads(zv);
     }
-
-    // ---------------- z taps: complete the oldest queue entry, shift the others
+    release();
+    VT eo[Tr::NACC][RY];
+    ztaps(zv, emit, eo);
+    if (emit) {
 #pragma unroll
-    for (int a = 0; a < Tr::NACC; ++a) {
-      const T sgn = (OP == CURL && a == 0) ? (T)-1 : (T)1;
-      if (emit) {  // output plane zc - P
+      for (int a = 0; a < Tr::NACC; ++a)
 #pragma unroll
-        for (int j = 0; j < RY; ++j) {
-          VT o;
-          fma_to(o, sgn * A0.c[2 * P], zv[a][j], q[a][2 * P - 1][j]);
-          store(OP == CURL ? a + 1 : 0, zc - P, j, o);
-        }
-      }
-#pragma unroll
-      for (int i = 2 * P - 1; i >= 1; --i)
-#pragma unroll
-        for (int j = 0; j < RY; ++j) fma_to(q[a][i][j], sgn * A0.c[i], zv[a][j], q[a][i - 1][j]);
-#pragma unroll
-      for (int j = 0; j < RY; ++j) fma_vec<true>(q[a][0][j], sgn * A0.c[0], zv[a][j]);
+        for (int j = 0; j < RY; ++j) store(OP == CURL ? a + 1 : 0, zc - P, j, eo[a][j]);
     }
-    if constexpr (OP != GRAD) {
-      if (inr && !zb) {  // in-plane part of plane zc joins its output (which has just received tap P)
-#pragma unroll
-        for (int a = 0; a < Tr::NACC; ++a)
-#pragma unroll
-          for (int j = 0; j < RY; ++j) add_vec(q[a][P][j], tin[a][j]);
-      }
-    }
+    if (inr && !zb) join(tin);
   }
 }
 
@@ -978,6 +1164,12 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     if (((n2 - xl_last) / XV - 1) % CFG::LX < CFG::RY - 1) ok = false;  // the helper lanes sit in the owner's warp
     if (env_int("FDX_XBAND_SLOW", 0)) ok = false;
     prm.xfast = ok ? 1 : 0, prm.xnt_l = ntl, prm.xnt_r = ntr;
+    prm.plain_ok = env_int("FDX_FUSED_NOPLAIN", 0) ? 0 : 1;
+    prm.dbg = env_int("FDX_FUSED_DBG", 0);
+    prm.rim_first = env_int("FDX_FUSED_RIMFIRST", 1);
+    // direct x bands: every tap of every band row lies inside the owner's window of 2 HXV + 1 vectors
+    prm.xdirect = (ok && (px->nl - 1) + (ntl - 1) <= G::HX + XV - 1 && (px->nr - 1) + (ntr - 1) <= G::HX + XV - 1 &&
+                   !env_int("FDX_XBAND_NODIRECT", 0)) ? 1 : 0;
   }
   prm.z_begin = sl.z_begin, prm.z_end = sl.z_end;
   prm.tz_off = -sl.in_first;
@@ -996,12 +1188,17 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     if (px->nl > G::TX || px->wl > G::TX + G::HX || n2 - xl < px->nr || xl > n2 - px->wr + G::HX) return FDX_EUNSUPPORTED;
     if (px->nl * px->wl + px->nr * px->wr > kXTabMax) return FDX_EUNSUPPORTED;
   }
-  const int nz = sl.z_end - sl.z_begin;
   const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
-  // z chunking.  Every chunk pays 2P warm-up planes, so long chunks are cheaper, but the launch ends
-  // when its last CTA does: the chunks are graded -- long ones first, then medium, and the CTAs of the
-  // last ~1.5 waves are short -- which keeps both the redundancy and the tail small.
+  // z chunking.  The planes next to a physical z boundary (one-sided taps, gathered directly) form
+  // two chunks of their own, launched first, so that every other chunk is free of them and can take
+  // the specialised march.  Every chunk pays 2P warm-up planes, so long chunks are cheaper, but the
+  // launch ends when its last CTA does: the chunks are graded -- long ones first, then medium, and
+  // the CTAs of the last ~1.5 waves are short -- which keeps both the redundancy and the tail small.
   {
+    const bool zsplit = !env_int("FDX_FUSED_ZB_MERGE", 0);
+    const int zlo_end = zsplit ? std::min(sl.z_end, std::max(sl.z_begin, plans[0]->nl)) : sl.z_begin;     // [z_begin, zlo_end): left band planes
+    const int zhi_beg = zsplit ? std::max(zlo_end, std::min(sl.z_end, n0 - plans[0]->nr)) : sl.z_end;  // [zhi_beg, z_end): right band planes
+    const int nz = zhi_beg - zlo_end;                                                     // planes of the graded middle part
     const int64_t slots = (int64_t)kNumSMs * CFG::MINB;
     int L = env_int("FDX_FUSED_CHUNK", 0), S = env_int("FDX_FUSED_CHUNK_SHORT", 0);
     const bool uniform = L > 0 && S <= 0;  // an explicit chunk alone means uniform chunks (sweeps)
@@ -1010,7 +1207,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     if (uniform) S = L;
     if (L > kMaxPlanes - 2 * P) L = kMaxPlanes - 2 * P;
     if (S > L) S = L;
-    if ((int64_t)nz > (int64_t)L * (kMaxCuts - 28)) L = (int)((nz + kMaxCuts - 29) / (kMaxCuts - 28));
+    if ((int64_t)nz > (int64_t)L * (kMaxCuts - 30)) L = (int)((nz + kMaxCuts - 31) / (kMaxCuts - 30));
     if (L > kMaxPlanes - 2 * P) return FDX_EUNSUPPORTED;
     // small grids: keep at least ~2 waves of CTAs
     while (!uniform && L > S && tiles * ((nz + L - 1) / L) < 2 * slots) L = L / 2 > S ? L / 2 : S;
@@ -1019,7 +1216,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     if (!uniform && L == S)
       while (S > 4 && tiles * ((nz + S - 1) / S) < 2 * slots) S = L = (S / 2 > 4 ? S / 2 : 4);
     if (S > L) S = L;
-    // sizes from the end of the z range backwards: short layers, as many medium ones, then long ones
+    // sizes from the end of the middle range backwards: short layers, as many medium ones, then long ones
     int sizes[kMaxCuts];
     int n = 0, rem = nz;
     int n_short = (int)((3 * slots + 2 * tiles - 1) / (2 * tiles));  // ~1.5 waves of CTAs
@@ -1037,7 +1234,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     }
     if (const char* cuts = std::getenv("FDX_FUSED_CUTS")) {  // experiments: explicit sizes, last z chunk first
       n = 0, rem = nz;
-      for (const char* c = cuts; *c && rem > 0 && n < kMaxCuts - 1;) {
+      for (const char* c = cuts; *c && rem > 0 && n < kMaxCuts - 3;) {
         int v = std::atoi(c);
         if (v <= 0) break;
         if (v > kMaxPlanes - 2 * P) v = kMaxPlanes - 2 * P;
@@ -1046,23 +1243,28 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
         while (*c && *c != ',') ++c;
         if (*c == ',') ++c;
       }
-      while (rem > 0 && n < kMaxCuts) {
+      while (rem > 0 && n < kMaxCuts - 2) {
         const int v = rem < L ? rem : L;
         sizes[n++] = v, rem -= v;
       }
       if (rem > 0) return FDX_EUNSUPPORTED;
     }
-    if (n > kMaxCuts) return FDX_EUNSUPPORTED;
-    // launch order: the first chunk, the last one (both touch the physical boundary, whose one-sided
-    // planes are slow), then the others in z order -- long to short
-    int zstart[kMaxCuts], zlen[kMaxCuts];
-    int z = sl.z_begin;
-    for (int i = n - 1, k = 0; i >= 0; --i, ++k) zstart[k] = z, zlen[k] = sizes[i], z += sizes[i];
+    if (n > kMaxCuts - 2) return FDX_EUNSUPPORTED;
+    // launch order: the two band chunks (their one-sided planes are slow), then the middle in z order --
+    // long to short
     int k = 0;
-    prm.cut_z[k] = zstart[0], prm.cut_n[k] = (short)zlen[0], ++k;
-    if (n > 1) prm.cut_z[k] = zstart[n - 1], prm.cut_n[k] = (short)zlen[n - 1], ++k;
-    for (int i = 1; i + 1 < n; ++i) prm.cut_z[k] = zstart[i], prm.cut_n[k] = (short)zlen[i], ++k;
-    prm.n_chunks = n;
+    if (zlo_end > sl.z_begin) prm.cut_z[k] = sl.z_begin, prm.cut_n[k] = (short)(zlo_end - sl.z_begin), ++k;
+    if (sl.z_end > zhi_beg) prm.cut_z[k] = zhi_beg, prm.cut_n[k] = (short)(sl.z_end - zhi_beg), ++k;
+    int z = zlo_end;
+    if (!zsplit && n > 1) {  // (experiment) the old order: first and last chunk first
+      prm.cut_z[k] = zlo_end, prm.cut_n[k] = (short)sizes[n - 1], ++k;
+      prm.cut_z[k] = zhi_beg - sizes[0], prm.cut_n[k] = (short)sizes[0], ++k;
+      z += sizes[n - 1];
+      for (int i = n - 2; i >= 1; --i) prm.cut_z[k] = z, prm.cut_n[k] = (short)sizes[i], ++k, z += sizes[i];
+    } else
+    for (int i = n - 1; i >= 0; --i) prm.cut_z[k] = z, prm.cut_n[k] = (short)sizes[i], ++k, z += sizes[i];
+    if (k == 0) return FDX_OK;  // nothing to do
+    prm.n_chunks = k;
   }
   const int64_t blocks = tiles * prm.n_chunks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
