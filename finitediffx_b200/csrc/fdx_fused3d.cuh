@@ -110,6 +110,7 @@ struct FusedParams {
   int plain_ok;  // interior CTAs may take the specialised (flag-free) march
   int rim_first;  // launch order inside a chunk layer: rim tiles first (FDX_FUSED_RIMFIRST=0 switches it off)
   int dbg;       // experiments only (FDX_FUSED_DBG): 2 no x-band work, 16 every tile takes the interior copy (both: wrong results at the edges)
+  int ydirect;   // ... and the tiles with y-band rows (the first / last tile row holds every band row and all of its taps)
   int xdirect;   // ... and so may the tiles with x-band columns (the owner's window holds all band taps)
   T xcl[kXT][kXV], xcr[kXT][kXV];
   short2 rng[kRowsMax];  // [first, last+1) nonzero band column of every band row
@@ -576,17 +577,39 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   };
   // y band of global row y: taps from the tile when it holds all of them, else from global memory.
   // tcol: generic address of (tile row 0, this thread's x); gcol: global address of (z, row 0, xg)
-  auto band_y = [&](const T* tcol, int pitch, int boxy, const T* gcol, int y) {
+  auto band_y = [&](const T* tcol, int pitch, int boxy, const T* gcol, int y, bool tile_only) {
     int tab, c0, c1, cb;
     band_rng(A1, y, tab, c0, c1, cb);
     VT a;
     const int r0 = cb - (y0 - P);  // tile row of band column 0
-    if (r0 + c0 >= 0 && r0 + c1 <= boxy) {
+    if (tile_only || (r0 + c0 >= 0 && r0 + c1 <= boxy)) {  // (tile_only: host-checked, prm.ydirect)
       const T* p = tcol + r0 * pitch;
       a = band_dot_vec(tab, c0, c1, [&](int c) { return *reinterpret_cast<const VT*>(p + c * pitch); });
     } else {
       const T* p = gcol + (int64_t)cb * n2;
       a = band_dot_vec(tab, c0, c1, [&](int c) { return ld_cached<T, V>(p + (int64_t)c * n2); });
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) a.v[v] *= A1.alpha;
+    return a;
+  };
+  // y band of global row y from the tile alone (specialised march; host-checked, prm.ydirect): one 128-bit
+  // shared load and one coefficient per tap, taps in ascending order like band_dot_vec (same bits).
+  // tcol: shared address of (tile row 0, this thread's x) of the field
+  auto band_y_tile = [&](uint32_t tcol, int pitch_b, int y) {
+    int tab, c0, c1, cb;
+    band_rng(A1, y, tab, c0, c1, cb);
+    uint32_t addr = tcol + (uint32_t)((cb - (y0 - P) + c0) * pitch_b);
+    VT a;
+#pragma unroll
+    for (int v = 0; v < V; ++v) a.v[v] = 0;
+#pragma unroll 2
+    for (int c = c0; c < c1; ++c) {
+      const T cf = prm.tab[tab + c];
+      const VT x = lds_vec<T, V>(addr);
+#pragma unroll
+      for (int v = 0; v < V; ++v) a.v[v] = fma(cf, x.v[v], a.v[v]);
+      addr += (uint32_t)pitch_b;
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) a.v[v] *= A1.alpha;
@@ -872,7 +895,8 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // z-band planes take the generic march below).
   const int nout = ze - zs;
   const bool fast_ok = prm.plain_ok && (x0 + G::TX <= x_hi) && (y0 + G::TY <= n1) && zs >= A0.nl && ze <= n0 - A0.nr &&
-                       n_planes == nout + 2 * P && (!(xedge_l || xedge_r) || prm.xdirect || (prm.dbg & 16));
+                       n_planes == nout + 2 * P && (!(xedge_l || xedge_r) || prm.xdirect || (prm.dbg & 16)) &&
+                       (!yedge || prm.ydirect || (prm.dbg & 16));
   if (fast_ok) {
     uint64_t oz[Tr::NOUT][RY];
 #pragma unroll
@@ -895,16 +919,15 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
         VT ya[NY][RY], xa[NX][RY], ip[NIP + 1][RY];
         hot_inplane(zv, ya, xa, xe);
         if (ye) {
-          if (yband) {
-            const int64_t zofs = (int64_t)(zin0 + it) * plane;
+          if (yband && !(prm.dbg & 4)) {
 #pragma unroll
             for (int qq = 0; qq < NY; ++qq) {
               const int f = IP::yfield(qq);
-              const T* tile = reinterpret_cast<const T*>(smem_raw + (ring - smem0) + soff + G::field_off(f));
+              // (tile row 0, this thread's x) = this thread's vector in tile row ty * RY, moved up
+              const uint32_t tcol = tb[f] + soff - (uint32_t)(ty * RY * G::box_x(f) * (int)sizeof(T));
 #pragma unroll
               for (int j = 0; j < RY; ++j)
-                if (is_yband(j))
-                  ya[qq][j] = band_y(tile + G::xoff(f) + tx * V, G::box_x(f), G::box_y(f), prm.in[f] + zofs + xg, yg + j);
+                if (is_yband(j)) ya[qq][j] = band_y_tile(tcol, G::box_x(f) * (int)sizeof(T), yg + j);
             }
           }
         }
@@ -932,10 +955,10 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 #pragma unroll
         for (int j = 0; j < RY; ++j) oz[o][j] += (uint64_t)plane_b;
     };
-    if (edge && !(prm.dbg & 16)) {
+    if ((edge && !(prm.dbg & 16)) || nout < P) {
 #pragma unroll 1
       for (int k = n_planes; k > 0; --k) step(true, 0);
-    } else if (nout >= P) {
+    } else {
 #pragma unroll 1
       for (int k = 0; k < P; ++k) step(false, 1);
 #pragma unroll 1
@@ -944,9 +967,6 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       for (int k = nout - P; k > 0; --k) step(false, 3);
 #pragma unroll 1
       for (int k = 0; k < P; ++k) step(false, 4);
-    } else {
-#pragma unroll 1
-      for (int k = n_planes; k > 0; --k) step(true, 0);
     }
     return;
   }
@@ -985,7 +1005,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 #pragma unroll
             for (int j = 0; j < RY; ++j)
               if (is_yband(j))
-                ya[qq][j] = band_y(tile(f) + G::xoff(f) + tx * V, G::box_x(f), G::box_y(f), prm.in[f] + zofs + xg, yg + j);
+                ya[qq][j] = band_y(tile(f) + G::xoff(f) + tx * V, G::box_x(f), G::box_y(f), prm.in[f] + zofs + xg, yg + j, false);
           }
         }
         if (xedge_l || xedge_r) {
@@ -1165,6 +1185,10 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     if (env_int("FDX_XBAND_SLOW", 0)) ok = false;
     prm.xfast = ok ? 1 : 0, prm.xnt_l = ntl, prm.xnt_r = ntr;
     prm.plain_ok = env_int("FDX_FUSED_NOPLAIN", 0) ? 0 : 1;
+    {
+      const fdx_plan_s* py = plans[1];
+      prm.ydirect = (py->nl <= G::TY && py->nr <= G::TY && py->wl <= G::TY + P && py->wr <= G::TY + P) ? 1 : 0;
+    }
     prm.dbg = env_int("FDX_FUSED_DBG", 0);
     prm.rim_first = env_int("FDX_FUSED_RIMFIRST", 1);
     // direct x bands: every tap of every band row lies inside the owner's window of 2 HXV + 1 vectors
