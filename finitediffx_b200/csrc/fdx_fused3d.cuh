@@ -1190,7 +1190,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
       prm.ydirect = (py->nl <= G::TY && py->nr <= G::TY && py->wl <= G::TY + P && py->wr <= G::TY + P) ? 1 : 0;
     }
     prm.dbg = env_int("FDX_FUSED_DBG", 0);
-    prm.rim_first = env_int("FDX_FUSED_RIMFIRST", 1);
+    prm.rim_first = -1;  // decided below, once the tile counts are known
     // direct x bands: every tap of every band row lies inside the owner's window of 2 HXV + 1 vectors
     prm.xdirect = (ok && (px->nl - 1) + (ntl - 1) <= G::HX + XV - 1 && (px->nr - 1) + (ntr - 1) <= G::HX + XV - 1 &&
                    !env_int("FDX_XBAND_NODIRECT", 0)) ? 1 : 0;
@@ -1213,6 +1213,9 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     if (px->nl * px->wl + px->nr * px->wr > kXTabMax) return FDX_EUNSUPPORTED;
   }
   const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
+  // rim tiles first only while a layer of tiles fits the machine (measured: +3 % at 512^3 = 256 tiles per layer,
+  // -3 % at 1024^3 = 1024 tiles, where launching the rim apart from its neighbours costs L2 halo sharing)
+  prm.rim_first = env_int("FDX_FUSED_RIMFIRST", tiles <= (int64_t)kNumSMs * CFG::MINB ? 1 : 0);
   // z chunking.  The planes next to a physical z boundary (one-sided taps, gathered directly) form
   // two chunks of their own, launched first, so that every other chunk is free of them and can take
   // the specialised march.  Every chunk pays 2P warm-up planes, so long chunks are cheaper, but the

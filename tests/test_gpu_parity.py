@@ -431,3 +431,41 @@ def test_tiny_and_thin_grids_take_the_fused_path():
         out = _call("laplacian", x, **kw)
         assert _cabi.last_kernel().startswith("fused_"), (shape, _cabi.last_kernel())
         assert parity_error("laplacian", x, kw, out, O.laplacian(x, **kw)) <= 1e-5, shape
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_specialised_marches_match_the_generic_march_and_the_oracle(dtype):
+    """Interior tiles, rim tiles (in-register x bands, tile y bands, corners) and the chunks of z-band
+    planes take different code copies of the fused kernels.  On grids with at least three tiles each way
+    (and on partial last tiles, which stay generic) they must agree BIT FOR BIT with the generic march
+    (FDX_FUSED_NOPLAIN=1), with the merged z-band chunks of the old chunk list, with either launch order,
+    and meet the parity bound against the oracle."""
+    rng = np.random.default_rng(11)
+    for shape, accs in (((40, 56, 200), (2, 4, 6)), ((33, 50, 264), (4,)), ((21, 97, 196), (2, 6))):
+        x = rng.standard_normal(shape).astype(dtype)
+        f = rng.standard_normal((3,) + shape).astype(dtype)
+        for acc in accs:
+            for op, arr, kw in (("laplacian", x, dict(accuracy=acc, step_size=0.25)), ("divergence", f, dict(accuracy=acc, step_size=(0.1, 0.2, 0.3), keepdims=False)),
+                                ("gradient", x, dict(accuracy=acc, step_size=0.25)), ("curl", f, dict(accuracy=acc, step_size=0.25))):
+                out = _call(op, arr, **kw)
+                assert _cabi.last_kernel().startswith("fused_"), (op, shape, acc, _cabi.last_kernel())
+                err = parity_error(op, arr, kw, out, getattr(O, op)(arr, **kw))
+                assert err <= TOL[np.dtype(dtype)], (op, shape, acc, err)
+                for env in (dict(FDX_FUSED_NOPLAIN=1), dict(FDX_FUSED_ZB_MERGE=1), dict(FDX_FUSED_RIMFIRST=0), dict(FDX_FUSED_RIMFIRST=1),
+                            dict(FDX_XBAND_NODIRECT=1), dict(FDX_FUSED_CHUNK=5), dict(FDX_FUSED_NOPLAIN=1, FDX_FUSED_ZB_MERGE=1, FDX_FUSED_CHUNK=9)):
+                    with _env(**env):
+                        other = _call(op, arr, **kw)
+                    assert np.array_equal(out, other), (op, shape, acc, env, float(np.abs(out - other).max()))
+
+
+def test_z_extents_around_the_band_planes():
+    """n0 from `all planes are band planes` upwards: the z-band chunks, an empty or one-plane middle part."""
+    rng = np.random.default_rng(12)
+    for acc in (2, 4):
+        p = (2 + acc) // 2
+        for n0 in range(2 + acc + p - 1, 2 + acc + p + 9):  # from the smallest axis the reference accepts (p + L)
+            x = rng.standard_normal((n0, 48, 72))
+            kw = dict(accuracy=acc, step_size=0.5)
+            out = _call("laplacian", x, **kw)
+            err = parity_error("laplacian", x, kw, out, O.laplacian(x, **kw))
+            assert err <= 1e-12, (n0, acc, err, _cabi.last_kernel())
