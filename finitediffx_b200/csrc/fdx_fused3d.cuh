@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
@@ -1229,7 +1230,16 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     const int64_t slots = (int64_t)kNumSMs * CFG::MINB;
     int L = env_int("FDX_FUSED_CHUNK", 0), S = env_int("FDX_FUSED_CHUNK_SHORT", 0);
     const bool uniform = L > 0 && S <= 0;  // an explicit chunk alone means uniform chunks (sweeps)
-    if (L <= 0) L = 64 > 8 * P ? 64 : 8 * P;
+    if (L <= 0) {
+      // long chunks: 2P warm-up planes per chunk against the imbalance of long CTAs near the end of the launch.
+      // L* = sqrt(2P nz tiles / (4 x 148)) fits the B200 sweeps (512^3: 40 at P = 3, 32 at P = 2; 1024^3: the cap)
+      const int cap = 64 > 8 * P ? 64 : 8 * P;
+      const double lstar = std::sqrt(2.0 * P * (double)(nz > 0 ? nz : 1) * (double)tiles / (4.0 * kNumSMs));
+      L = ((int)(lstar + 2.0) / 4) * 4;
+      if (L > cap) L = cap;
+      if (L < 16) L = 16;
+      if (L < 4 * P) L = 4 * P;
+    }
     if (S <= 0) S = 16 > 4 * P ? 16 : 4 * P;
     if (uniform) S = L;
     if (L > kMaxPlanes - 2 * P) L = kMaxPlanes - 2 * P;
