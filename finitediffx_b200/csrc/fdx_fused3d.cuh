@@ -895,9 +895,13 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // copies: interior tiles and tiles with band rows / columns (partial tiles and the chunks that hold
   // z-band planes take the generic march below).
   const int nout = ze - zs;
+  // the rim copy takes its y bands from the tile alone: every band row of this tile must find all of its taps in
+  // the tile's rows [y0 - P, y0 + TY + P)
+  const bool ytile_ok = prm.ydirect && (!(y0 < A1.nl) || (y0 <= P && A1.wl <= y0 + G::TY + P)) &&
+                        (!(y0 + G::TY > n1 - A1.nr) || (n1 - A1.wr >= y0 - P && n1 <= y0 + G::TY + P));
   const bool fast_ok = prm.plain_ok && (x0 + G::TX <= x_hi) && (y0 + G::TY <= n1) && zs >= A0.nl && ze <= n0 - A0.nr &&
                        n_planes == nout + 2 * P && (!(xedge_l || xedge_r) || prm.xdirect || (prm.dbg & 16)) &&
-                       (!yedge || prm.ydirect || (prm.dbg & 16));
+                       (!yedge || ytile_ok || (prm.dbg & 16));
   if (fast_ok) {
     uint64_t oz[Tr::NOUT][RY];
 #pragma unroll

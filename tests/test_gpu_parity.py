@@ -469,3 +469,41 @@ def test_z_extents_around_the_band_planes():
             out = _call("laplacian", x, **kw)
             err = parity_error("laplacian", x, kw, out, O.laplacian(x, **kw))
             assert err <= 1e-12, (n0, acc, err, _cabi.last_kernel())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_adjoints_through_every_march(dtype):
+    """Transposed plans have wide bands (P + L rows, up to 2L + 1 taps): band rows may straddle tiles and
+    their taps may leave the tile (n1 = 20 with 16-row tiles: the right band of the FIRST tile reaches row 19).
+    vjp of every fused operator: specialised marches == generic march bit for bit, and both agree with the
+    composition of axis kernels (FDX_FUSED_DISABLE) within the parity bound; dot-product identity in float64."""
+    torch.manual_seed(5)
+    tol = 2e-5 if dtype == torch.float32 else 1e-12
+    for shape in ((33, 20, 132), (24, 20, 200), (40, 56, 200), (21, 97, 196), (19, 36, 72)):
+        x = torch.randn(shape, device="cuda", dtype=dtype)
+        f = torch.randn((3,) + shape, device="cuda", dtype=dtype)
+        for acc in (2, 4):
+            for op, arr in (("laplacian", x), ("gradient", x), ("divergence", f), ("curl", f)):
+                kw = dict(accuracy=acc, step_size=(0.1, 0.2, 0.3))
+                if op == "divergence":
+                    kw["keepdims"] = False
+
+                def vjp(seed=3):
+                    a = arr.clone().requires_grad_(True)
+                    out = getattr(fdx, op)(a, **kw)
+                    g = torch.randn(out.shape, device="cuda", dtype=dtype, generator=torch.Generator(device="cuda").manual_seed(seed))
+                    (ga,) = torch.autograd.grad(out, a, g)
+                    return out.detach(), g, ga
+
+                out, g, ga = vjp()
+                assert _cabi.last_kernel().startswith("fused_"), (op, shape, acc, _cabi.last_kernel())
+                with _env(FDX_FUSED_NOPLAIN=1):
+                    _, _, ga_generic = vjp()
+                assert torch.equal(ga, ga_generic), (op, shape, acc, (ga - ga_generic).abs().max().item())
+                with _env(FDX_FUSED_DISABLE=1):
+                    _, _, ga_axis = vjp()
+                scale = ga_axis.abs().max().item()
+                assert (ga - ga_axis).abs().max().item() <= tol * 50 * scale, (op, shape, acc, (ga - ga_axis).abs().max().item() / scale)
+                if dtype == torch.float64:
+                    lhs, rhs = float((out * g).sum()), float((arr * ga).sum())
+                    assert abs(lhs - rhs) <= 1e-10 * max(1.0, abs(lhs)), (op, shape, acc, lhs, rhs)

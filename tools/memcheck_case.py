@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import finitediffx_b200 as fdx
 torch.manual_seed(0)
-for shape in [(40, 36, 72), (33, 20, 132), (16, 16, 64), (70, 17, 12)]:
+for shape in [(40, 36, 72), (33, 20, 132), (16, 16, 64), (70, 17, 12), (40, 56, 200), (21, 97, 196)]:  # the last two have interior, rim and corner tiles
     for dt in (torch.float32, torch.float64):
         x = torch.randn(shape, device="cuda", dtype=dt)
         F = torch.randn((3,) + shape, device="cuda", dtype=dt)
