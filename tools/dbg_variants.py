@@ -26,14 +26,26 @@ op = args[0] if len(args) > 0 else "laplacian"
 acc = int(args[1]) if len(args) > 1 else 4
 dt = torch.float64 if (len(args) > 2 and args[2] == "f64") else torch.float32
 n = int(args[3]) if len(args) > 3 else 512
+vjp = op.endswith("_vjp")
+if vjp:
+    op = op[:-4]
 fin = 3 if op in ("divergence", "curl") else 1
 shape = (n, n, n) if fin == 1 else (3, n, n, n)
 xs = [torch.randn(shape, device="cuda", dtype=dt) for _ in range(3)]
 h = 1.0 / (n - 1)
-def call(x):
+def fwd(x):
     if op == "divergence":
         return fdx.divergence(x, accuracy=acc, step_size=h, keepdims=False)
     return getattr(fdx, op)(x, accuracy=acc, step_size=h)
+if vjp:
+    xr = xs[0].requires_grad_(True)
+    out0 = fwd(xr)
+    gs = [torch.randn_like(out0) for _ in range(3)]
+    it = iter(range(10**9))
+    def call(x):
+        return torch.autograd.grad(out0, xr, gs[next(it) % 3], retain_graph=True)
+else:
+    call = fwd
 variants = [("default", {})]
 for sp in specs:
     name, _, kv = sp.partition(":")
