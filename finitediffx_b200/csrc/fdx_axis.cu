@@ -18,12 +18,58 @@
 
 namespace fdx {
 
+// ---------------------------------------------------------------------------------- band rows
+// The few boundary rows with their own dense taps.  One element per thread; `g` numbers the band elements of the
+// whole array.  Runs as the leading CTAs of the main kernels (FusedBand: one launch per call, the band rows'
+// latency hides behind the main rows) or as a kernel of its own behind the shape/alignment fallbacks.
+template <typename T>
+struct FusedBand {
+  Bands b;
+  T alpha;
+  int64_t n, inner, outer;
+  int blocks;  // leading CTAs that work on band elements (0: the caller launches axis_band_kernel)
+};
+
+template <typename T, bool ACC>
+__device__ __forceinline__ void band_element(const T* __restrict__ x, T* __restrict__ out, int64_t n, int64_t inner,
+                                             int64_t outer, const Bands& b, T alpha, int64_t g) {
+  const int nb = b.nl + b.nr;
+  if (g >= outer * nb * inner) return;
+  const int64_t j = g % inner;
+  const int64_t rest = g / inner;
+  const int bi = (int)(rest % nb);
+  const int64_t o = rest / nb;
+  int64_t row, col0;
+  int w;
+  const double* coef;
+  if (bi < b.nl) {
+    row = bi, col0 = 0, w = b.wl, coef = b.l + (int64_t)bi * b.wl;
+  } else {
+    const int r = bi - b.nl;
+    row = n - b.nr + r, col0 = n - b.wr, w = b.wr, coef = b.r + (int64_t)r * b.wr;
+  }
+  const T* xp = x + (o * n + col0) * inner + j;
+  T acc = 0;
+  for (int c = 0; c < w; ++c) {
+    const T cf = (T)__ldg(coef + c);
+    if (cf != (T)0) acc = fma(cf, __ldg(xp + (int64_t)c * inner), acc);
+  }
+  acc *= alpha;
+  T* o_ptr = out + (o * n + row) * inner + j;
+  *o_ptr = ACC ? *o_ptr + acc : acc;
+}
+
 // ------------------------------------------------------------------------------- axis_stream
 template <typename T, int V, int W, bool ACC>
 __global__ void __launch_bounds__(128) axis_stream_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n,
                                                           int64_t inner_v, int lo, int r0, int r1, int rows_per_chunk,
-                                                          int n_chunks, int64_t n_tiles, const __grid_constant__ Taps<T> taps) {
-  int64_t b = blockIdx.x;
+                                                          int n_chunks, int64_t n_tiles, const __grid_constant__ Taps<T> taps,
+                                                          const __grid_constant__ FusedBand<T> fb) {
+  if ((int)blockIdx.x < fb.blocks) {
+    band_element<T, ACC>(x, out, fb.n, fb.inner, fb.outer, fb.b, fb.alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    return;
+  }
+  int64_t b = (int64_t)blockIdx.x - fb.blocks;
   const int64_t tile = b % n_tiles;
   b /= n_tiles;
   const int c = (int)(b % n_chunks);
@@ -88,8 +134,13 @@ __host__ __device__ constexpr int floor_div(int a, int b) { return (a >= 0) ? a 
 
 template <typename T, int V, int LO, int HI, bool ACC>
 __global__ void __launch_bounds__(256) axis_row_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t total_vecs,
-                                                       int n_v, int r0, int r1, const __grid_constant__ Taps<T> taps) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                       int n_v, int r0, int r1, const __grid_constant__ Taps<T> taps,
+                                                       const __grid_constant__ FusedBand<T> fb) {
+  if ((int)blockIdx.x < fb.blocks) {
+    band_element<T, ACC>(x, out, fb.n, fb.inner, fb.outer, fb.b, fb.alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    return;
+  }
+  const int64_t g = ((int64_t)blockIdx.x - fb.blocks) * blockDim.x + threadIdx.x;
   if (g >= total_vecs) return;
   const int64_t row = g / n_v;
   const int t = (int)(g - row * n_v);
@@ -150,37 +201,25 @@ __global__ void __launch_bounds__(256) axis_row_scalar_kernel(const T* __restric
 template <typename T, bool ACC>
 __global__ void __launch_bounds__(256) axis_band_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n,
                                                         int64_t inner, int64_t outer, Bands b, T alpha) {
-  const int nb = b.nl + b.nr;
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= outer * nb * inner) return;
-  const int64_t j = g % inner;
-  const int64_t rest = g / inner;
-  const int bi = (int)(rest % nb);
-  const int64_t o = rest / nb;
-  int64_t row, col0;
-  int w;
-  const double* coef;
-  if (bi < b.nl) {
-    row = bi, col0 = 0, w = b.wl, coef = b.l + (int64_t)bi * b.wl;
-  } else {
-    const int r = bi - b.nl;
-    row = n - b.nr + r, col0 = n - b.wr, w = b.wr, coef = b.r + (int64_t)r * b.wr;
-  }
-  const T* xp = x + (o * n + col0) * inner + j;
-  T acc = 0;
-  for (int c = 0; c < w; ++c) {
-    const T cf = (T)__ldg(coef + c);
-    if (cf != (T)0) acc = fma(cf, __ldg(xp + (int64_t)c * inner), acc);
-  }
-  acc *= alpha;
-  T* o_ptr = out + (o * n + row) * inner + j;
-  *o_ptr = ACC ? *o_ptr + acc : acc;
+  band_element<T, ACC>(x, out, n, inner, outer, b, alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// The band rows as leading CTAs of a main kernel with `threads` threads per CTA (blocks = 0 if there are none or
+// too many; the caller then launches axis_band_kernel).
+template <typename T>
+static FusedBand<T> fused_band(const fdx_plan_s* p, int64_t outer, int64_t inner, double alpha, int threads) {
+  FusedBand<T> fb;
+  fb.b = bands_of(p), fb.alpha = (T)alpha, fb.n = p->n, fb.inner = inner, fb.outer = outer, fb.blocks = 0;
+  const int64_t total = outer * (int64_t)(p->nl + p->nr) * inner;
+  const int64_t blocks = (total + threads - 1) / threads;
+  if (blocks > 0 && blocks <= (1 << 20)) fb.blocks = (int)blocks;
+  return fb;
 }
 
 // ----------------------------------------------------------------------------------- dispatch
 template <typename T, int V, int W, bool ACC>
 static int launch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool* band_done) {
   const int r0 = p->nl, r1 = p->n - p->nr;
   const int m = r1 - r0;
   if (m <= 0) return FDX_OK;
@@ -195,21 +234,23 @@ static int launch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer,
   rows = ((rows + W - 1) / W) * W;
   if (rows > m) rows = m;
   const int n_chunks = (m + rows - 1) / rows;
-  const int64_t blocks = n_tiles * n_chunks * outer;
+  const FusedBand<T> fb = fused_band<T>(p, outer, inner, alpha, 128);
+  const int64_t blocks = n_tiles * n_chunks * outer + fb.blocks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   axis_stream_kernel<T, V, W, ACC><<<(unsigned)blocks, 128, 0, st>>>(x, out, p->n, inner_v, p->lo, r0, r1, rows, n_chunks,
-                                                                     n_tiles, scaled_taps<T>(p, alpha));
+                                                                     n_tiles, scaled_taps<T>(p, alpha), fb);
   count_launch("axis_stream");
+  *band_done = fb.blocks > 0;
   return FDX_OK;
 }
 
 template <typename T, int V, bool ACC>
 static int dispatch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool* band_done) {
   switch (p->hi - p->lo + 1) {
 #define FDX_CASE(W_) \
   case W_:           \
-    return launch_stream<T, V, W_, ACC>(p, x, out, outer, inner, alpha, st);
+    return launch_stream<T, V, W_, ACC>(p, x, out, outer, inner, alpha, st, band_done);
     FDX_CASE(2) FDX_CASE(3) FDX_CASE(4) FDX_CASE(5) FDX_CASE(6) FDX_CASE(7) FDX_CASE(8) FDX_CASE(9) FDX_CASE(10)
     FDX_CASE(11) FDX_CASE(12) FDX_CASE(13)
 #undef FDX_CASE
@@ -219,25 +260,27 @@ static int dispatch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t oute
 }
 
 template <typename T, int V, int LO, int HI, bool ACC>
-static int launch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st) {
+static int launch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done) {
   const int n_v = p->n / V;
   const int64_t total = outer * n_v;
-  const int64_t blocks = (total + 255) / 256;
+  const FusedBand<T> fb = fused_band<T>(p, outer, 1, alpha, 256);
+  const int64_t blocks = (total + 255) / 256 + fb.blocks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   axis_row_kernel<T, V, LO, HI, ACC><<<(unsigned)blocks, 256, 0, st>>>(x, out, total, n_v, p->nl, p->n - p->nr,
-                                                                       scaled_taps<T>(p, alpha));
+                                                                       scaled_taps<T>(p, alpha), fb);
   count_launch("axis_row");
+  *band_done = fb.blocks > 0;
   return FDX_OK;
 }
 
 template <typename T, int V, bool ACC>
-static int dispatch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st) {
+static int dispatch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done) {
   const int lo = p->lo, hi = p->hi;
 #define FDX_C(P_) \
-  if (lo == -P_ && hi == P_) return launch_row<T, V, -P_, P_, ACC>(p, x, out, outer, alpha, st);
+  if (lo == -P_ && hi == P_) return launch_row<T, V, -P_, P_, ACC>(p, x, out, outer, alpha, st, band_done);
 #define FDX_F(L_)                                                                              \
-  if (lo == 0 && hi == L_) return launch_row<T, V, 0, L_, ACC>(p, x, out, outer, alpha, st); \
-  if (lo == -L_ && hi == 0) return launch_row<T, V, -L_, 0, ACC>(p, x, out, outer, alpha, st);
+  if (lo == 0 && hi == L_) return launch_row<T, V, 0, L_, ACC>(p, x, out, outer, alpha, st, band_done); \
+  if (lo == -L_ && hi == 0) return launch_row<T, V, -L_, 0, ACC>(p, x, out, outer, alpha, st, band_done);
   FDX_C(1) FDX_C(2) FDX_C(3) FDX_C(4) FDX_C(5) FDX_C(6)
   FDX_F(1) FDX_F(2) FDX_F(3) FDX_F(4) FDX_F(5) FDX_F(6) FDX_F(7) FDX_F(8) FDX_F(9) FDX_F(10) FDX_F(11)
 #undef FDX_C
@@ -252,15 +295,16 @@ static int apply_impl(const fdx_plan_s* p, const T* x, T* out, int64_t outer, in
   const int m = p->n - p->nl - p->nr;
   const bool aligned16 = (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
   int rc = FDX_OK;
+  bool band_done = false;  // the band rows rode along with the main kernel
   if (m > 0) {
     if (inner > 1) {
       if (aligned16 && inner % V == 0)
-        rc = dispatch_stream<T, V, ACC>(p, x, out, outer, inner, alpha, st);
+        rc = dispatch_stream<T, V, ACC>(p, x, out, outer, inner, alpha, st, &band_done);
       else
-        rc = dispatch_stream<T, 1, ACC>(p, x, out, outer, inner, alpha, st);
+        rc = dispatch_stream<T, 1, ACC>(p, x, out, outer, inner, alpha, st, &band_done);
     } else {
       rc = FDX_EUNSUPPORTED;
-      if (aligned16 && p->n % V == 0) rc = dispatch_row<T, V, ACC>(p, x, out, outer, alpha, st);
+      if (aligned16 && p->n % V == 0) rc = dispatch_row<T, V, ACC>(p, x, out, outer, alpha, st, &band_done);
       if (rc == FDX_EUNSUPPORTED) {
         const int64_t total = outer * m;
         const int64_t blocks = (total + 255) / 256;
@@ -275,7 +319,7 @@ static int apply_impl(const fdx_plan_s* p, const T* x, T* out, int64_t outer, in
     FDX_LAUNCH_CHECK();
   }
   const int nb = p->nl + p->nr;
-  if (nb > 0) {
+  if (nb > 0 && !band_done) {
     const int64_t total = outer * nb * inner;
     const int64_t blocks = (total + 255) / 256;
     if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
