@@ -901,7 +901,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   const bool ytile_ok = prm.ydirect && (!(y0 < A1.nl) || (y0 <= P && A1.wl <= y0 + G::TY + P)) &&
                         (!(y0 + G::TY > n1 - A1.nr) || (n1 - A1.wr >= y0 - P && n1 <= y0 + G::TY + P));
   const bool fast_ok = prm.plain_ok && (x0 + G::TX <= x_hi) && (y0 + G::TY <= n1) && zs >= A0.nl && ze <= n0 - A0.nr &&
-                       n_planes == nout + 2 * P &&
+                       n_planes == nout + 2 * P && (!(xedge_l || xedge_r) || prm.xdirect || (prm.dbg & 48)) &&
                        (!yedge || ytile_ok || (prm.dbg & 16));
   if (fast_ok) {
     uint64_t oz[Tr::NOUT][RY];
@@ -934,16 +934,6 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 #pragma unroll
               for (int j = 0; j < RY; ++j)
                 if (is_yband(j)) ya[qq][j] = band_y_tile(tcol, G::box_x(f) * (int)sizeof(T), yg + j);
-            }
-          }
-        }
-        if (xe) {
-          // wide x bands (adjoint plans): rows the owner's window cannot serve go through the warp-cooperative path
-          if ((xedge_l || xedge_r) && !prm.xdirect && !(prm.dbg & 32)) {
-#pragma unroll
-            for (int qq = 0; qq < NX; ++qq) {
-              const int f = IP::xfield(qq);
-              xband_coop(ring + soff + G::field_off(f) + (uint32_t)(G::yoff(f) * G::box_x(f) * sizeof(T)), G::box_x(f), xa[qq]);
             }
           }
         }
