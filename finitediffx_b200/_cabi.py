@@ -322,3 +322,29 @@ def fused3d_ptr(kind: str, plans: Sequence[AxisPlan], in_ptrs: Sequence[int], ou
         return rc
     check(rc, f"fdx_{kind}3d (slab)")
     return 0
+
+
+def prepare_fused3d_ptr(kind: str, plans: Sequence[AxisPlan], in_ptrs: Sequence[int], out_ptrs: Sequence[int], alpha: Sequence[float],
+                        dtype: torch.dtype, device: torch.device, z_begin: int, z_end: int, in_first: int, in_planes: int,
+                        out_first: int):
+    """``fused3d_ptr`` with every ctypes object built once: returns ``launch(stream_ptr: int) -> None`` for callers
+    that repeat the same slab call on fixed buffers (the multi-GPU step: three launches per 0.2 ms of GPU work)."""
+    keep, hp = _handles(plans, device)
+    sfx = "f32" if dtype == torch.float32 else "f64"
+    slab = Slab(int(z_begin), int(z_end), int(in_first), int(in_planes), int(out_first))
+    fn = getattr(load(), f"fdx_{kind}3d_{sfx}")
+
+    def arr(ptrs):
+        ptrs = list(ptrs) + [0] * (3 - len(ptrs))
+        return (C.c_void_p * 3)(*[C.c_void_p(int(p)) for p in ptrs])
+
+    xin = C.c_void_p(int(in_ptrs[0])) if kind in ("laplacian", "gradient") else arr(in_ptrs)
+    xout = C.c_void_p(int(out_ptrs[0])) if kind in ("laplacian", "divergence") else arr(out_ptrs)
+    al, sref = _alphas(alpha), C.byref(slab)
+
+    def launch(stream_ptr: int, _keep=(keep, slab, xin, xout, al)):
+        rc = fn(hp, xin, xout, al, sref, C.c_void_p(stream_ptr))
+        if rc != 0:
+            check(rc, f"fdx_{kind}3d (slab)")
+
+    return launch

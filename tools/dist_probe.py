@@ -19,7 +19,7 @@ t_cpu = time.perf_counter() - t0
 torch.cuda.synchronize()
 t_all = time.perf_counter() - t0
 if rank == 0: print(f"world {world}: CPU enqueue {t_cpu/K*1e6:.1f} us/step, total {t_all/K*1e6:.1f} us/step")
-graph_ok = os.environ.get("PROBE_GRAPH", "1") == "1"
+graph_ok = os.environ.get("PROBE_GRAPH", "0") == "1"  # (the process-group teardown hangs after an NCCL capture on this stack)
 if graph_ok:
     try:
         graphs = []
