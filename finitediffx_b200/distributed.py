@@ -103,11 +103,12 @@ class SlabOperator:
         depth = self.owned + 2 * self.P
         self.inputs = [[torch.zeros((depth, n1, n2), dtype=dtype, device=device) for _ in range(nin)] for _ in range(n_buffers)]
         self.outputs = [[torch.empty((self.owned, n1, n2), dtype=dtype, device=device) for _ in range(nout)] for _ in range(n_buffers)]
-        self.comm = torch.cuda.Stream(device) if device.type == "cuda" else None
+        # high priority: the exchange and the shells must not queue behind the thousands of CTAs of the interior kernel
+        self.comm = torch.cuda.Stream(device, priority=-1) if device.type == "cuda" else None
         self.ev_halo = torch.cuda.Event() if device.type == "cuda" else None
         # the two shells run on their own stream: they become runnable as soon as the halos have landed
         # and fill the tail of the interior kernel instead of following it
-        self.shell = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.shell = torch.cuda.Stream(device, priority=-1) if device.type == "cuda" else None
         self.ev_shell = torch.cuda.Event() if device.type == "cuda" else None
         zf_n = len(Z_FIELDS[kind])
         # bytes this rank receives (= sends) per step
