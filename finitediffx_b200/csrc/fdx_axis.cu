@@ -11,8 +11,10 @@
 //   axis_row     (axis IS the contiguous one)
 //       one thread owns 16 bytes of outputs and gathers its window with aligned 128-bit loads;
 //       the overlap between neighbouring threads is served by L1.
-//   axis_band    the few boundary rows with their own dense taps (one-sided stencils,
-//       finite_diff.py:75-78,85-88 etc., or the wider bands of a transposed plan).
+//   band rows    the few boundary rows with their own dense taps (one-sided stencils,
+//       finite_diff.py:75-78,85-88 etc., or the wider bands of a transposed plan): they ride along as
+//       the leading CTAs of the two kernels above (one launch per call); axis_band is the same code as a
+//       kernel of its own behind the fallbacks.
 //   *_scalar     shape/alignment fallbacks of the above (still CUDA, never the host).
 #include "fdx_common.cuh"
 
