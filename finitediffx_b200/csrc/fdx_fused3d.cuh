@@ -1195,7 +1195,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
       const fdx_plan_s* py = plans[1];
       prm.ydirect = (py->nl <= G::TY && py->nr <= G::TY && py->wl <= G::TY + P && py->wr <= G::TY + P) ? 1 : 0;
     }
-    prm.dbg = env_int("FDX_FUSED_DBG", 0);
+    prm.dbg = env_int("FDX_FUSED_EXPERIMENTS", 0) ? env_int("FDX_FUSED_DBG", 0) : 0;  // (wrong results at the rim: timing experiments only)
     prm.rim_first = -1;  // decided below, once the tile counts are known
     // direct x bands: every tap of every band row lies inside the owner's window of 2 HXV + 1 vectors
     prm.xdirect = (ok && (px->nl - 1) + (ntl - 1) <= G::HX + XV - 1 && (px->nr - 1) + (ntr - 1) <= G::HX + XV - 1 &&

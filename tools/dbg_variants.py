@@ -4,6 +4,7 @@
 Variants run interleaved for several rounds so that clock drift hits all of them alike; min and median are reported.
 """
 import os, sys, json, statistics
+os.environ["FDX_FUSED_EXPERIMENTS"] = "1"  # lets FDX_FUSED_DBG through (timing experiments: wrong results at the rim)
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import finitediffx_b200 as fdx
