@@ -366,7 +366,11 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // before the next tile's origin, so no output is written twice
   const int x_shift = max(0, n2 - G::TX);
   const int x0 = min(tile_x * G::TX, x_shift), y0 = tile_y * G::TY;
-  const int x_hi = tile_x + 1 < prm.tiles_x ? min((tile_x + 1) * G::TX, x_shift) : n2;
+  // ... except that with two tiles the first one keeps every left band column (wide adjoint bands may reach past
+  // the origin of the shifted tile): the cut between the two is max(x_shift, nl rounded up to a vector)
+  const int x_cut2 = min(G::TX, max(x_shift, ((prm.ax[2].nl + V - 1) / V) * V));
+  const int x_hi = tile_x + 1 < prm.tiles_x ? (prm.tiles_x == 2 ? x_cut2 : min((tile_x + 1) * G::TX, x_shift)) : n2;
+  const int x_lo = (prm.tiles_x == 2 && tile_x == 1) ? x_cut2 : x0;  // first column this tile writes
   const int zs = prm.cut_z[cslot];
   const int ze = zs + prm.cut_n[cslot];
   const int zin0 = max(zs - P, prm.z_lo);
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // row j of this thread lies inside the grid: bit j (opaque, so that it stays one register)
   uint32_t rmask = 0;
 #pragma unroll
-  for (int j = 0; j < RY; ++j) rmask |= ((xg < x_hi) && (yg + j < n1)) ? (1u << j) : 0u;
+  for (int j = 0; j < RY; ++j) rmask |= ((xg >= x_lo) && (xg < x_hi) && (yg + j < n1)) ? (1u << j) : 0u;
   asm volatile("" : "+r"(rmask));
   auto rok = [&](int j) { return (rmask >> j) & 1u; };
 
@@ -900,7 +904,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // the tile's rows [y0 - P, y0 + TY + P)
   const bool ytile_ok = prm.ydirect && (!(y0 < A1.nl) || (y0 <= P && A1.wl <= y0 + G::TY + P)) &&
                         (!(y0 + G::TY > n1 - A1.nr) || (n1 - A1.wr >= y0 - P && n1 <= y0 + G::TY + P));
-  const bool fast_ok = prm.plain_ok && (x0 + G::TX <= x_hi) && (y0 + G::TY <= n1) && zs >= A0.nl && ze <= n0 - A0.nr &&
+  const bool fast_ok = prm.plain_ok && (x0 + G::TX <= x_hi) && (x_lo == x0) && (y0 + G::TY <= n1) && zs >= A0.nl && ze <= n0 - A0.nr &&
                        n_planes == nout + 2 * P && (!(xedge_l || xedge_r) || prm.xdirect || (prm.dbg & 48)) &&
                        (!yedge || ytile_ok || (prm.dbg & 16));
   if (fast_ok) {
@@ -1217,6 +1221,10 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     const int xl = n2 > G::TX ? n2 - G::TX : 0;  // origin of the (shifted) last tile
     if (px->nl > G::TX || px->wl > G::TX + G::HX || n2 - xl < px->nr || xl > n2 - px->wr + G::HX) return FDX_EUNSUPPORTED;
     if (px->nl * px->wl + px->nr * px->wr > kXTabMax) return FDX_EUNSUPPORTED;
+    if (prm.tiles_x == 2) {  // the cut between the first tile and the shifted second one (see the kernel): the right band
+      const int cut = std::min(G::TX, std::max(xl, ((px->nl + G::V - 1) / G::V) * G::V));  // must lie behind it
+      if (n2 - px->nr < cut) return FDX_EUNSUPPORTED;
+    }
   }
   const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
   // rim tiles first only while a layer of tiles fits the machine (measured: +3 % at 512^3 = 256 tiles per layer,

@@ -479,7 +479,8 @@ def test_adjoints_through_every_march(dtype):
     composition of axis kernels (FDX_FUSED_DISABLE) within the parity bound; dot-product identity in float64."""
     torch.manual_seed(5)
     tol = 2e-5 if dtype == torch.float32 else 1e-12
-    for shape in ((33, 20, 132), (24, 20, 200), (40, 56, 200), (21, 97, 196), (19, 36, 72)):
+    # (84, 51, 68) fp32: two x tiles, the shifted second one starts at column 4 -- inside the 6-column adjoint band
+    for shape in ((33, 20, 132), (24, 20, 200), (40, 56, 200), (21, 97, 196), (19, 36, 72), (84, 51, 68), (30, 24, 36)):
         x = torch.randn(shape, device="cuda", dtype=dtype)
         f = torch.randn((3,) + shape, device="cuda", dtype=dtype)
         for acc in (2, 4):
