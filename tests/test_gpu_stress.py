@@ -1,0 +1,60 @@
+"""Randomised shapes: the fused 3-D kernels (every march, forward and vjp) against the composition of axis
+kernels inside the same library (FDX_FUSED_DISABLE=1).  `tools/stress_shapes.py` is the long form of this
+test; it found the two-tile ownership bug of wide adjoint bands (n2 = 68, fp32)."""
+import os
+import random
+
+import pytest
+import torch
+
+import finitediffx_b200 as fdx
+from finitediffx_b200 import _cabi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_shapes_fused_vs_axis_kernels(seed):
+    rnd = random.Random(seed)
+    for case in range(30):
+        dtype = rnd.choice([torch.float32, torch.float64])
+        V = 4 if dtype == torch.float32 else 2
+        acc = rnd.choice([2, 4, 4, 6])
+        lo = 2 * acc + 2
+        if rnd.random() < 0.5:
+            n0 = rnd.randint(lo, 40)
+            n1 = max(lo, rnd.choice([15, 16, 17, 31, 32, 33, 48, 49]))
+            n2 = max(V * ((lo + V - 1) // V), V * rnd.choice([8, 15, 16, 17, 18, 31, 32, 33, 34, 49]))
+        else:
+            n0, n1, n2 = rnd.randint(lo, 60), rnd.randint(lo, 90), V * rnd.randint((lo + V - 1) // V, 200 // V)
+        op = rnd.choice(["laplacian", "gradient", "divergence", "curl"])
+        h = (rnd.uniform(0.05, 0.5), rnd.uniform(0.05, 0.5), rnd.uniform(0.05, 0.5))
+        shape = (n0, n1, n2) if op in ("laplacian", "gradient") else (3, n0, n1, n2)
+        x = torch.randn(shape, device="cuda", dtype=dtype)
+        kw = dict(accuracy=acc, step_size=h)
+        if op == "divergence":
+            kw["keepdims"] = False
+
+        def run():
+            a = x.clone().requires_grad_(True)
+            out = getattr(fdx, op)(a, **kw)
+            k = _cabi.last_kernel()
+            g = torch.randn(out.shape, device="cuda", dtype=dtype, generator=torch.Generator(device="cuda").manual_seed(case))
+            (ga,) = torch.autograd.grad(out, a, g)
+            return out.detach(), ga, k
+
+        old = os.environ.get("FDX_FUSED_DISABLE")
+        try:
+            os.environ["FDX_FUSED_DISABLE"] = "0"
+            out, ga, k = run()
+            os.environ["FDX_FUSED_DISABLE"] = "1"
+            out_r, ga_r, _ = run()
+        finally:
+            if old is None:
+                os.environ.pop("FDX_FUSED_DISABLE", None)
+            else:
+                os.environ["FDX_FUSED_DISABLE"] = old
+        tol = 3e-5 if dtype == torch.float32 else 2e-11
+        e1 = ((out - out_r).abs().max() / out_r.abs().max()).item()
+        e2 = ((ga - ga_r).abs().max() / ga_r.abs().max()).item()
+        assert e1 <= tol and e2 <= tol, (case, op, dtype, acc, (n0, n1, n2), k, e1, e2)

@@ -16,9 +16,19 @@ for case in range(cases):
     dtype = rnd.choice([torch.float32, torch.float64])
     V = 4 if dtype == torch.float32 else 2
     acc = rnd.choice([2, 2, 4, 4, 6, 8])
-    n0 = rnd.randint(2 * acc + 4, 90)
-    n1 = rnd.randint(2 * acc + 4, 130)
-    n2 = V * rnd.randint((2 * acc + 4 + V - 1) // V, 330 // V)
+    lo = 2 * acc + 2  # the adjoint bands need p + L rows per side
+    mode = rnd.random()
+    if mode < 0.25:  # thin in one or two directions
+        n0, n1, n2 = rnd.randint(lo, lo + 6), rnd.randint(lo, 130), V * rnd.randint((lo + V - 1) // V, 330 // V)
+    elif mode < 0.5:  # around the tile sizes (64 x 16 fp32, 32 x 16 fp64) and their multiples
+        n0 = rnd.randint(lo, 70)
+        n1 = rnd.choice([15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65]) + rnd.choice([0, 0, 16])
+        n2 = V * rnd.choice([8, 15, 16, 17, 18, 31, 32, 33, 34, 48, 49, 64, 65]) * rnd.choice([1, 1, 2])
+        n1, n2 = max(n1, lo), max(n2, V * ((lo + V - 1) // V))
+    else:
+        n0 = rnd.randint(lo, 90)
+        n1 = rnd.randint(lo, 130)
+        n2 = V * rnd.randint((lo + V - 1) // V, 330 // V)
     op = rnd.choice(["laplacian", "gradient", "divergence", "curl"])
     h = (rnd.uniform(0.05, 0.5), rnd.uniform(0.05, 0.5), rnd.uniform(0.05, 0.5))
     shape = (n0, n1, n2) if op in ("laplacian", "gradient") else (3, n0, n1, n2)
