@@ -1265,6 +1265,9 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     // 35 -> 16 us for the README's 100^3 divergence): many very short chunks until two waves are filled
     if (!uniform && L == S)
       while (S > 4 && tiles * ((nz + S - 1) / S) < 2 * slots) S = L = (S / 2 > 4 ? S / 2 : 4);
+    // ... but never more chunks than the cut table holds (few tiles and a long z axis, e.g. 512 x 80 x 192: the
+    // launch used to be refused and the call fell back to the three-pass composition)
+    if ((int64_t)nz > (int64_t)L * (kMaxCuts - 30)) L = (int)((nz + kMaxCuts - 31) / (kMaxCuts - 30));
     if (S > L) S = L;
     // sizes from the end of the middle range backwards: short layers, as many medium ones, then long ones
     int sizes[kMaxCuts];

@@ -425,7 +425,8 @@ def test_x_band_paths_and_awkward_tiles(dtype):
 def test_tiny_and_thin_grids_take_the_fused_path():
     """Grids of a few tiles (very short z chunks) and slabs thinner than a tile."""
     rng = np.random.default_rng(8)
-    for shape in ((8, 8, 8), (9, 300, 16), (300, 9, 16), (16, 9, 300), (100, 100, 100)):
+    # (520, 24, 64): few tiles and a long z axis -- the very short chunks of tiny grids must not overflow the cut table
+    for shape in ((8, 8, 8), (9, 300, 16), (300, 9, 16), (16, 9, 300), (100, 100, 100), (520, 24, 64)):
         x = rng.standard_normal(shape).astype(np.float32)
         kw = dict(accuracy=2, step_size=0.5)
         out = _call("laplacian", x, **kw)
