@@ -79,3 +79,29 @@ def test_host_streaming_fp64_against_the_oracle():
     np.testing.assert_allclose(out[sub], ref, rtol=1e-12, atol=1e-9)
     ref0 = O.laplacian(x[:24], accuracy=2, step_size=0.5)[:12]
     np.testing.assert_allclose(out[:12], ref0, rtol=1e-12, atol=1e-9)
+
+
+def test_eight_slabs_of_a_few_tile_grid_equal_the_public_operator():
+    """512 x 80 x 192 fp32 laplacian in 8 slabs (tools/dist_check.py at 8 ranks, emulated): few tiles and a long z axis.
+    The whole-grid call once overflowed the table of z cuts and fell back to the three-pass composition, which differs
+    from the fused slab launches in the last bit; both must be the fused kernel and agree exactly."""
+    torch.manual_seed(3)
+    world, n1, n2, acc, h = 8, 80, 192, 4, (0.1, 0.2, 0.3)
+    n0 = 64 * world
+    x = torch.randn((n0, n1, n2), device="cuda")
+    ref = fdx.laplacian(x, accuracy=acc, step_size=h)
+    assert _cabi.last_kernel() == "fused_laplacian3d", _cabi.last_kernel()
+    spec = fs.make_spec("laplacian", (n0, n1, n2), accuracy=acc, step_size=h)
+    P = spec.radius
+    per = n0 // world
+    for r in range(world):
+        z0, z1 = r * per, (r + 1) * per
+        ins = torch.zeros((per + 2 * P, n1, n2), device="cuda")
+        lo_b, hi_b = max(0, z0 - P), min(n0, z1 + P)
+        ins[lo_b - (z0 - P) : hi_b - (z0 - P)] = x[lo_b:hi_b]
+        out = torch.empty((per, n1, n2), device="cuda")
+        lo, hi = z0 + (P if r > 0 else 0), z1 - (P if r < world - 1 else 0)
+        for a, b in ((lo, hi), (z0, lo), (hi, z1)):
+            if b > a:
+                fs.run_slab(spec, [ins], z0 - P, [out], z0, a, b)
+        assert torch.equal(out, ref[z0:z1]), r
