@@ -1415,8 +1415,12 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
         return launch_cfg<OP, T, P, Cfg<16, 16, 1, 4, (P <= 3 ? 2 : 1)>>(plans, in, out, alpha, sl, st);
     }
   } else if constexpr (OP == LAP && sizeof(T) == 4 && P <= 3) {
-    switch (cfg) {
+    // wide x bands (transposed plans: P + L band columns) go through the warp-cooperative path, whose cost per warp
+    // grows with the rows a warp covers: full-width warps (LX = 16, 4 rows) halve it
+    const bool wide = plans[2]->nl > 16 / (int)sizeof(T) || plans[2]->nr > 16 / (int)sizeof(T);
+    switch (cfg == 0 && wide && !env_int("FDX_FUSED_NOWIDECFG", 0) ? 2 : cfg) {
       FDX_CFG(1, 16, 8, 2, 4, 3)
+      FDX_CFG(2, 16, 8, 2, 8, 4, 16)
       default:
         return launch_cfg<OP, T, P, Cfg<16, 8, 2, 8, 4, 8>>(plans, in, out, alpha, sl, st);
     }
