@@ -58,3 +58,57 @@ def test_random_shapes_fused_vs_axis_kernels(seed):
         e1 = ((out - out_r).abs().max() / out_r.abs().max()).item()
         e2 = ((ga - ga_r).abs().max() / ga_r.abs().max()).item()
         assert e1 <= tol and e2 <= tol, (case, op, dtype, acc, (n0, n1, n2), k, e1, e2)
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_random_operators_vs_oracle(seed):
+    """Random small N-D shapes, axes, derivatives, accuracies and methods of every public operator against the
+    oracle on the parity metric (axis kernels with their band rows riding along, accumulate paths, scalar
+    fallbacks for unaligned shapes, 2-D curl, jacobian / hessian compositions)."""
+    import numpy as np
+
+    from oracle import fdx_oracle as O
+    from tests._parity import TOL, parity_error
+
+    rnd = random.Random(seed)
+    rng = np.random.default_rng(seed)
+    done = 0
+    for case in range(70):
+        dtype = rnd.choice([np.float32, np.float64])
+        method = rnd.choice(["central", "central", "forward", "backward"])
+        acc = rnd.randint(1, 6)
+        op = rnd.choice(["difference", "difference", "laplacian", "gradient", "divergence", "curl", "jacobian", "hessian"])
+        big = lambda: rnd.randint(2 * (acc + 3) + 1, 40)  # long enough for every stencil of this accuracy
+        if op == "difference":
+            nd = rnd.randint(1, 4)
+            shape = tuple(big() for _ in range(nd))
+            kw = dict(axis=rnd.randrange(-nd, nd), derivative=rnd.randint(1, 3), accuracy=acc, method=method, step_size=rnd.uniform(0.1, 2.0))
+        elif op in ("laplacian", "gradient"):
+            nd = rnd.randint(1, 3)
+            shape = tuple(big() for _ in range(nd))
+            kw = dict(accuracy=acc, method=method, step_size=tuple(rnd.uniform(0.1, 2.0) for _ in range(nd)))
+        elif op == "divergence":
+            nd = rnd.randint(2, 3)
+            shape = (nd + rnd.randint(0, 1),) + tuple(big() for _ in range(nd))
+            kw = dict(accuracy=acc, method=method, step_size=rnd.uniform(0.1, 2.0), keepdims=rnd.random() < 0.5)
+        elif op == "curl":
+            nd = rnd.randint(2, 3)
+            shape = (nd,) + tuple(big() for _ in range(nd))
+            kw = dict(accuracy=acc, method=method, step_size=rnd.uniform(0.1, 2.0))
+        elif op == "jacobian":
+            nd = rnd.randint(2, 3)
+            shape = (rnd.randint(1, 3),) + tuple(big() for _ in range(nd))
+            kw = dict(accuracy=acc, method=method, step_size=rnd.uniform(0.1, 2.0))
+        else:  # hessian: 2-D (the 3-D key collision of the reference is covered elsewhere)
+            shape = (big(), big())
+            kw = dict(accuracy=max(acc, 2), method=method, step_size=rnd.uniform(0.1, 2.0))
+        x = rng.standard_normal(shape).astype(dtype)
+        ref = getattr(O, op)(x, **kw)
+        out = getattr(fdx, op)(torch.from_numpy(x).cuda(), **kw).cpu().numpy()
+        assert out.shape == ref.shape and out.dtype == ref.dtype, (case, op, shape, kw)
+        err = parity_error(op, x, kw, out, ref)
+        # the reference's own float64 coefficients deviate from the exact ones for long stencils (DESIGN section 2)
+        tol = TOL[np.dtype(dtype)] if dtype == np.float32 else max(TOL[np.dtype(dtype)], 1e-12 * 10 ** max(0, kw.get("derivative", 1) + acc - 5))
+        assert err <= tol, (case, op, shape, kw, err)
+        done += 1
+    assert done == 70
