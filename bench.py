@@ -116,6 +116,23 @@ class ClockSampler:
         }
 
 
+def _config(name, world):
+    """The `config` object of the JSON line: a function of (workload, GPU count) only, so that both arms print the same."""
+    w = WORKLOADS[name]
+    n = w["n"]
+    strong = bool(w.get("strong"))
+    return {
+        "workload": name,
+        "grid": [n, n, n] if strong else [n * world, n, n],
+        "grid_per_gpu": [n // world, n, n] if strong else [n, n, n],
+        "accuracy": w["accuracy"],
+        "method": "central",
+        "step_size": f"1/{n - 1}",
+        "decomposition": "single GPU" if world == 1 else f"slab along axis 0, {world} ranks, NCCL halo exchange",
+        "l2": "one input slab per rank, far larger than L2 (126 MB)" if strong else "3 rotating inputs, each larger than L2 (126 MB); outputs freshly written",
+    }
+
+
 def _bytes_per_point(w):
     s = 4 if w["dtype"] == "f32" else 8
     return s * (w["fields_in"] + w["fields_out"])
@@ -198,8 +215,6 @@ def _cpu_step(w, n):
     def step():
         if w["op"] == "divergence":
             return OT.divergence(x, accuracy=w["accuracy"], step_size=h, keepdims=False)
-        if w["op"] == "curl":
-            raise NotImplementedError
         return getattr(OT, w["op"])(x, accuracy=w["accuracy"], step_size=h)
 
     return step
@@ -272,7 +287,7 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": w["dtype"],
         "data": "synthetic",
-        "config": {"workload": args.workload, "grid": [w["n"]] * 3, "accuracy": w["accuracy"], "method": "central"},
+        "config": _config(args.workload, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -388,21 +403,35 @@ def run_ours(args):
     else:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "slab data is device-resident at N>1 and for the strong-scaling workload; e2e is measured at N=1 on the headline workload"}
 
+    # ---- the other BASELINE configs, so that the driver's run holds their numbers too (all ranks take part at N>1)
+    peak, peak_src = _peaks()
+    extras = None
+    if not args.no_extras and args.workload == HEADLINE:
+        del inputs
+        if world > 1:
+            del op
+        torch.cuda.empty_cache()
+        try:
+            extras = _extras_single(fdx, _cabi, dev, peak) if world == 1 else _extras_multi(world, rank, dev, dist, peak)
+        except Exception as e:  # the headline line must not be lost to an extra (e.g. a smaller-memory GPU)
+            extras = {"error": repr(e)[:300]}
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = _peaks()
     alg_bytes = _bytes_per_point(w) * pts_per_gpu
     achieved = alg_bytes / (secs / args.steps) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if world == 1 and os.path.exists(tpath):  # per-launch DRAM bytes of the single-GPU kernel from its ncu --set full capture
         try:
-            traffic = json.load(open(tpath)).get(args.workload)
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get(args.workload), tj.get("_source")
         except Exception:
             traffic = None
+    config = _config(args.workload, world)
     line = {
         "metric": METRIC if w["op"] == "laplacian" else f"{w['op']}_gpts_per_s",
         "value": value,
@@ -416,20 +445,12 @@ def run_ours(args):
         "vs_baseline": None,
         "dtype": w["dtype"],
         "data": "synthetic",
-        "config": {
-            "workload": args.workload,
-            "grid": [n, n, n] if strong else [n * world, n, n],
-            "grid_per_gpu": [n // world, n, n] if strong else [n, n, n],
-            "accuracy": w["accuracy"],
-            "method": "central",
-            "step_size": f"1/{n - 1}",
-            "decomposition": "single GPU" if world == 1 else f"slab along axis 0, {world} ranks, NCCL halo exchange" + (", step replayed from a CUDA graph" if graphed else ""),
-            "l2": "one input slab per rank, far larger than L2 (126 MB)" if strong else "3 rotating inputs, each larger than L2 (126 MB); outputs freshly written",
-        },
+        "config": config,
+        "graph_replay": graphed,
         "clocks": sampler.summary() if sampler else None,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "kernel": _cabi.last_kernel(),
+        "kernel": "fused_" + w["op"] + "3d",
         "roofline": {
             "bound": "hbm",
             "achieved": achieved,
@@ -440,35 +461,12 @@ def run_ours(args):
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes,
             "traffic": traffic,
+            "traffic_source": traffic_src,
         },
     }
     if world == 1 and not args.no_cpu and not strong:
         line["cpu_baseline"] = _cpu_baseline(w)
-    if world == 1 and args.extras and not strong:
-        extras = {}
-        for name in ("divergence_512_f32_a4", "gradient_512_f32_a4", "curl_512_f32_a4", "laplacian_512_f64_a8"):
-            if name == args.workload:
-                continue
-            we = WORKLOADS[name]
-            del inputs
-            torch.cuda.empty_cache()
-            inputs = [_make_input(we, dev, seed=s) for s in range(2)]
-            s = _time_device(lambda x: _call(fdx, we, x), inputs, 20, 5)
-            ach = _bytes_per_point(we) * we["n"] ** 3 / (s / 20) / 1e9
-            extras[name] = {"gpts_per_s": we["n"] ** 3 * 20 / s / 1e9, "ms": s / 20 * 1e3, "hbm_gbs": ach, "frac": ach / peak, "kernel": _cabi.last_kernel()}
-        # laplacian forward + vjp (jax.grad through the custom_vjp analogue)
-        del inputs
-        torch.cuda.empty_cache()
-        x = _make_input(w, dev, seed=0).requires_grad_(True)
-        gcot = _make_input(w, dev, seed=1)
-
-        def fwd_bwd(_):
-            out = _call(fdx, w, x)
-            (gx,) = torch.autograd.grad(out, x, gcot)
-            return gx
-
-        s = _time_device(fwd_bwd, [0], 20, 5)
-        extras["laplacian_512_f32_a4_fwd_plus_vjp"] = {"gpts_per_s": n**3 * 20 / s / 1e9, "ms": s / 20 * 1e3}
+    if extras is not None:
         line["extras"] = extras
     print(json.dumps(line), flush=True)
     if dist:
@@ -482,6 +480,147 @@ def run_ours(args):
     return 0
 
 
+# ------------------------------------------------------------------------------ extras: every BASELINE config
+def _entry(pts, bytes_per_pt, secs_per_step, peak, kernel=None, **more):
+    gbs = pts * bytes_per_pt / secs_per_step / 1e9
+    e = {"ms": secs_per_step * 1e3, "gpts_per_s": pts / secs_per_step / 1e9, "hbm_gbs": gbs, "frac": gbs / peak, "frac_of_8TBs_nominal": gbs / 8000.0}
+    if kernel:
+        e["kernel"] = kernel
+    e.update(more)
+    return e
+
+
+def _extras_single(fdx, _cabi, dev, peak):
+    """Configs 1-5 of BASELINE.json on one GPU: device-resident, CUDA events, 5 warm-up + 20 timed steps each (inputs
+    far larger than L2, or three rotating inputs).  `frac` = algorithmic bytes / time / measured HBM peak."""
+    import torch
+
+    ex = {"note": "device-resident, CUDA events on the launching stream, 5 warm-up + 20 timed calls per case; frac = algorithmic bytes / time / measured HBM copy peak"}
+    K, W = 20, 5
+
+    def timed(fn, inputs, k=K, wu=W):
+        return _time_device(fn, inputs, k, wu) / k
+
+    # ---- config 3 (and the divergence half of the north-star target): 512^3 fp32, accuracy 4, forward and vjp
+    for name in ("divergence_512_f32_a4", "gradient_512_f32_a4", "curl_512_f32_a4", "laplacian_512_f64_a8"):
+        we = WORKLOADS[name]
+        inputs = [_make_input(we, dev, seed=s) for s in range(3)]
+        t = timed(lambda x: _call(fdx, we, x), inputs)
+        ex[name] = _entry(we["n"] ** 3, _bytes_per_point(we), t, peak, _cabi.last_kernel())
+        del inputs
+    for name in ("laplacian_512_f32_a4", "gradient_512_f32_a4", "divergence_512_f32_a4", "curl_512_f32_a4"):
+        we = WORKLOADS[name]
+        x = _make_input(we, dev, seed=0).requires_grad_(True)
+        out = _call(fdx, we, x)
+        gs = [torch.randn_like(out) for _ in range(3)]
+        t = timed(lambda g: torch.autograd.grad(out, x, g, retain_graph=True), gs)
+        ex[name + "_vjp"] = _entry(we["n"] ** 3, _bytes_per_point(we), t, peak, _cabi.last_kernel())
+        if name == HEADLINE:
+            def fwd_bwd(g):
+                o = _call(fdx, we, x)
+                return torch.autograd.grad(o, x, g)
+
+            t = timed(fwd_bwd, gs)
+            ex[name + "_fwd_plus_vjp"] = _entry(we["n"] ** 3, 2 * _bytes_per_point(we), t, peak)
+        del x, out, gs
+    # ---- the headline again: 200 steps back to back, and ~2 s of sustained load (SM clocks settle under power)
+    we = WORKLOADS[HEADLINE]
+    inputs = [_make_input(we, dev, seed=s) for s in range(3)]
+    t = timed(lambda x: _call(fdx, we, x), inputs, k=200, wu=20)
+    ex["laplacian_512_f32_a4_200_steps"] = _entry(we["n"] ** 3, _bytes_per_point(we), t, peak)
+    samp = ClockSampler(dev.index or 0)
+    t_all = _time_device(lambda x: _call(fdx, we, x), inputs, 8000, 2000, sampler=samp)
+    ex["laplacian_512_f32_a4_sustained"] = _entry(we["n"] ** 3, _bytes_per_point(we), t_all / 8000, peak, steps=8000, warmup=2000, clocks=samp.summary())
+    del inputs
+    torch.cuda.empty_cache()
+    # ---- config 1: README divergence (3, 100^3) fp32 accuracy 6: L2-resident, latency per call (host launch path included)
+    g = torch.linspace(0, 1, 100, device=dev)
+    X, Y, Z = torch.meshgrid(g, g, g, indexing="ij")
+    F = torch.stack([torch.sin(X) * torch.cos(Y), torch.cos(Y) * Z**2, torch.sin(Z) * X])
+    h = 1.0 / 99
+    t = timed(lambda f: fdx.divergence(f, accuracy=6, step_size=(h, h, h), keepdims=False), [F], k=200, wu=20)
+    ex["config1_divergence_100_f32_a6"] = {"us_per_call": t * 1e6, "gpts_per_s": 1e6 / t / 1e9, "kernel": _cabi.last_kernel(),
+                                           "note": "16 MB working set: L2-resident and launch-latency bound; back-to-back calls through the public API"}
+    del F, X, Y, Z
+    # ---- config 2: difference on (8192, 8192) fp32, all 168 cases (derivative 1-4, accuracy 2-8, three methods, both axes)
+    x = torch.randn((8192, 8192), device=dev)
+    per_axis = {0: [], 1: []}
+    for method in ("central", "forward", "backward"):
+        for d in range(1, 5):
+            for a in range(2, 9):
+                for axis in (0, 1):
+                    t = timed(lambda v: fdx.difference(v, axis=axis, accuracy=a, derivative=d, method=method, step_size=0.5), [x], k=10, wu=3)
+                    per_axis[axis].append((t, method, d, a))
+    pts = 8192 * 8192
+    for axis, rows in per_axis.items():
+        rows.sort()
+        med, worst, best = rows[len(rows) // 2], rows[-1], rows[0]
+        ex[f"config2_difference_8192sq_f32_axis{axis}"] = {
+            "cases": len(rows),
+            "median": _entry(pts, 8, med[0], peak),
+            "best": _entry(pts, 8, best[0], peak, case=list(best[1:])),
+            "worst": _entry(pts, 8, worst[0], peak, case=list(worst[1:])),
+            "note": "per call through the public API (host launch path included)",
+        }
+    del x
+    torch.cuda.empty_cache()
+    # ---- config 4: divergence / curl on a (3, 1024^3) fp32 field, accuracy 4 (one input: 12.9 GB, far larger than L2)
+    for name in ("divergence_1024_f32_a4_strong", "curl_1024_f32_a4_strong"):
+        we = WORKLOADS[name]
+        x = torch.empty((3, 1024, 1024, 1024), device=dev)
+        for c in range(3):
+            x[c].normal_()
+        t = timed(lambda v: _call(fdx, we, v), [x], k=10, wu=3)
+        ex["config4_" + name.replace("_strong", "")] = _entry(1024**3, _bytes_per_point(we), t, peak, _cabi.last_kernel())
+        del x
+        torch.cuda.empty_cache()
+    # ---- config 5: laplacian fp64 accuracy 8; one rank's slab of the 2048^3 grid at 8 GPUs (256 planes + 2 x 5 halo planes)
+    we = WORKLOADS["laplacian_2048_f64_a8_strong"]
+    x = torch.empty((266, 2048, 2048), device=dev, dtype=torch.float64)
+    x.normal_()
+    t = timed(lambda v: fdx.laplacian(v, accuracy=8, step_size=1.0 / 2047), [x], k=10, wu=3)
+    ex["config5_laplacian_f64_a8_slab_266x2048x2048"] = _entry(266 * 2048 * 2048, 16, t, peak, _cabi.last_kernel())
+    del x
+    torch.cuda.empty_cache()
+    return ex
+
+
+def _extras_multi(world, rank, dev, dist, peak):
+    """Strong scaling of BASELINE configs 4 and 5 over the N ranks of this run (device time, max over ranks), and -- the
+    honest overlap figure -- the same slab computed by rank 0 alone with no exchange (`slab_alone_ms`)."""
+    import torch
+
+    from finitediffx_b200 import distributed as fd
+
+    ex = {"note": "fixed global grids, slab-decomposed over the ranks of this run; ms = max over ranks, CUDA events, 3 warm-up + 10 timed steps; "
+                  "slab_alone_ms = this rank's planes (with halos in place) through the same kernel without any exchange"}
+    free_gb = torch.cuda.mem_get_info(dev)[0] / 1e9
+    for name in ("divergence_1024_f32_a4_strong", "curl_1024_f32_a4_strong", "laplacian_2048_f64_a8_strong"):
+        w = WORKLOADS[name]
+        n = w["n"]
+        esz = 4 if w["dtype"] == "f32" else 8
+        need_gb = (w["fields_in"] + w["fields_out"]) * esz * n**3 / world / 1e9 * 1.1
+        if n % world or need_gb > free_gb:
+            ex[name] = {"skipped": f"needs {need_gb:.0f} GB per rank"}
+            continue
+        dt = torch.float32 if w["dtype"] == "f32" else torch.float64
+        slab = fd.Slab(global_n0=n, rank=rank, world=world, group=dist.group.WORLD)
+        op = fd.SlabOperator(slab, w["op"], spatial=(n, n, n), dtype=dt, accuracy=w["accuracy"], step_size=1.0 / (n - 1), device=dev, n_buffers=1)
+        op.fill_random(0, seed=100 * rank)
+        secs = _time_device(lambda b: op.step(b), [0], 10, 3, barrier=lambda: dist.barrier())
+        t = torch.tensor([secs], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_s = float(t.item()) / 10
+        alone = _time_device(lambda b: op.step_alone(b), [0], 10, 3) / 10
+        dist.barrier()
+        e = _entry(n**3, _bytes_per_point(w), step_s, peak * world, n_gpus=world, slab_alone_ms=alone * 1e3, overlap_efficiency=alone / step_s,
+                   halo_bytes_per_step_per_rank=int(op.halo_bytes_per_step))
+        ex[name] = e
+        del op
+        torch.cuda.empty_cache()
+    return ex
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -489,7 +628,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
-    ap.add_argument("--extras", action="store_true", help="also time the other fused operators (N=1)")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip the other BASELINE configs (extras)")
+    ap.add_argument("--extras", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3:

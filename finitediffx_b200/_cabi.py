@@ -20,7 +20,8 @@ import torch
 
 from .plan import MAX_TAPS, AxisPlan
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libfdx_b200.so")
+# FDX_B200_LIB: another build of the same library (A/B timing of kernel variants, tools/ab_time.sh)
+_LIB_PATH = os.environ.get("FDX_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libfdx_b200.so")
 _lib = None
 _lock = threading.Lock()
 

@@ -411,7 +411,11 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   }
   __syncthreads();
 
-  // TMA issue (thread 0 only): plane `it` of this CTA's march goes to stage it % STAGES
+  // TMA issue (thread 0 only): plane `it` of this CTA's march goes to stage it % STAGES.
+  // (Round 2, measured and dropped: a non-blocking issue -- mbarrier.test_wait on the empty barrier, planes that cannot go
+  // out yet go out a step later, up to STAGES planes in flight.  ncu had shown thread 0's blocking wait on the empty
+  // barrier as the most-sampled stall, but that wait is benign -- warp 0 runs ahead of the slowest warp and the ring
+  // throttles it -- while the extra test / counter work sits on warp 0's critical path: laplacian fp32 -7 %, fp64 -8 %.)
   auto issue = [&](int it) {
     const int s = it % STAGES;
     if (it >= STAGES) mbar_wait_a(bar_empty + 8u * s, ((it / STAGES) - 1) & 1);  // all warps released it
@@ -502,12 +506,37 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 #pragma unroll
     for (int v = 0; v < V; ++v) w[HXV * V + v] = centre.v[v];
     VT r;
+    if constexpr (sizeof(T) == 4) {
+      // outputs (0,1) and (2,3): tap k of output v reads w[HX + v - P + k].  When that index is even for the first
+      // output of a pair, the two operands are an aligned register pair of the window and the tap is one packed
+      // FFMA2; the odd taps stay scalar (building their pairs would cost two register moves each: measured, no
+      // gain).  Per output the taps are summed in ascending order either way: the bits of the scalar form.
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      T s = A2.c[0] * w[HX + v - P];
+      for (int h = 0; h < 2; ++h) {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int k = 1; k < WZ; ++k) s = fma(A2.c[k], w[HX + v - P + k], s);
-      r.v[v] = s;
+        for (int k = 0; k < WZ; ++k) {
+          const int j = HX + 2 * h - P + k;
+          if (j % 2 == 0 && k > 0) {
+            unsigned long long a = pack2(s0, s1);
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(pack2(A2.c[k], A2.c[k])), "l"(pack2(w[j], w[j + 1])));
+            unpack2(a, s0, s1);
+          } else if (k == 0) {
+            s0 = A2.c[0] * w[j], s1 = A2.c[0] * w[j + 1];
+          } else {
+            s0 = fma(A2.c[k], w[j], s0), s1 = fma(A2.c[k], w[j + 1], s1);
+          }
+        }
+        r.v[2 * h] = s0, r.v[2 * h + 1] = s1;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        T s = A2.c[0] * w[HX + v - P];
+#pragma unroll
+        for (int k = 1; k < WZ; ++k) s = fma(A2.c[k], w[HX + v - P + k], s);
+        r.v[v] = s;
+      }
     }
     if (xb) {
       constexpr int XT = FusedParams<T>::kXT;

@@ -87,7 +87,8 @@ class SlabOperator:
     Device buffers (per rotating buffer set): inputs [P halo | owned | P halo] planes, outputs
     [owned] planes.  ``step(b)`` = halo exchange (comm stream) overlapped with the interior kernel;
     the two shells run on a third stream as soon as the halos have landed.  Requires owned >= 2P
-    and, on the end ranks, owned >= the width of the one-sided boundary band."""
+    and, on the end ranks, owned >= the width of the one-sided boundary band (its planes are read by the
+    interior launch, which does not wait for the halos)."""
 
     def __init__(self, sl: Slab, kind: str, spatial: Sequence[int], dtype: torch.dtype, *, accuracy: int, step_size,
                  device: torch.device, method: str = "central", n_buffers: int = 1):
@@ -97,7 +98,11 @@ class SlabOperator:
         p0 = self.spec.plans[0]
         self.P = max(-p0.lo, p0.hi)
         self.owned = sl.z1 - sl.z0
-        if self.owned < 2 * self.P or (sl.rank == 0 and self.owned + self.P < p0.wl) or (sl.upper is None and self.owned + self.P < p0.wr):
+        # The planes under the one-sided boundary stencils belong to the interior launch, which does not wait for the
+        # halo exchange: on the end ranks every plane those stencils read (wl / wr planes from the physical boundary)
+        # must be an OWNED plane, never a halo plane that NCCL may still be writing.
+        if self.owned < 2 * self.P or (sl.lower is None and sl.upper is not None and self.owned < p0.wl) or (
+                sl.upper is None and sl.lower is not None and self.owned < p0.wr):
             raise ValueError(f"slab of {self.owned} planes is too thin for stencil radius {self.P} / boundary bands {p0.wl},{p0.wr}")
         nin, nout = _slab.FIELDS[kind]
         depth = self.owned + 2 * self.P
@@ -187,9 +192,15 @@ class SlabOperator:
             shells.append(prep(z0, lo))
         if sl.upper is not None:
             shells.append(prep(hi, z1))
-        hit = (ops, interior, shells)
+        hit = (ops, interior, shells, prep(z0, z1))
         self._prep[b] = hit
         return hit
+
+    def step_alone(self, b: int = 0) -> List[torch.Tensor]:
+        """The same output planes in ONE launch with no exchange (the halo planes keep what the last exchange left):
+        the time of this rank's share of the kernel work alone, the reference point of the overlap efficiency."""
+        self._prepared(b)[3](torch.cuda.current_stream(self.device).cuda_stream)
+        return self.outputs[b]
 
     def step(self, b: int = 0) -> List[torch.Tensor]:
         sl = self.sl
@@ -197,7 +208,7 @@ class SlabOperator:
         outs = self.outputs[b]
         if self.device.type != "cuda":
             raise RuntimeError("SlabOperator.step needs CUDA buffers (there is no CPU path)")
-        ops, interior, shells = self._prepared(b)
+        ops, interior, shells, _ = self._prepared(b)
         has_nb = bool(shells)
         if has_nb:
             self.comm.wait_stream(cur)  # inputs of this step are ready

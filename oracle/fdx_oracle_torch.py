@@ -63,3 +63,14 @@ def gradient(x, *, accuracy=1, step_size=1, method="central"):
 
 def difference(x, **kw):
     return _difference(x, **kw)
+
+
+def curl(x, *, accuracy=1, step_size=1, method="central", keepdims=True):
+    """3-D curl as the reference composes it (finitediffx/_src/finite_diff.py:616-668): six differences, three
+    subtractions, one stack."""
+    if not (x.ndim == 4 and x.shape[0] == 3):
+        raise ValueError("the CPU arm times the 3-D curl only")
+    acc = O._per_axis(accuracy, 3, "accuracy")
+    step = O._per_axis(step_size, 3, "step_size")
+    d = lambda c, ax: _difference(x[c], axis=ax, accuracy=acc[ax], step_size=step[ax], derivative=1, method=method)
+    return torch.stack([d(2, 1) - d(1, 2), d(0, 2) - d(2, 0), d(1, 0) - d(0, 1)])

@@ -95,3 +95,21 @@ def test_input_planes_of_a_slab_call():
     assert spec.radius == 1 and spec.alpha == (10.0, 5.0, 1.0 / 0.3)
     with pytest.raises(ValueError):
         fs.make_spec("hessian", (64, 32, 32), accuracy=2, step_size=0.1)
+
+
+def test_thin_end_slabs_are_rejected():
+    """The interior launch of an end rank holds the planes under the one-sided boundary stencils and does not wait
+    for the halo exchange, so those stencils must read owned planes only: owned >= band width (P = 3: 8 planes).
+    owned = 6, 7 used to pass the check and race with the incoming halo."""
+    cpu = torch.device("cpu")
+    for owned, ok in ((6, False), (7, False), (8, True), (16, True)):
+        for rank in (0, 3):
+            sl = fd.Slab(global_n0=4 * owned, rank=rank, world=4)
+            if ok:
+                op = fd.SlabOperator(sl, "laplacian", (4 * owned, 16, 16), torch.float32, accuracy=4, step_size=0.1, device=cpu)
+                assert op.owned == owned and op.P == 3
+            else:
+                with pytest.raises(ValueError):
+                    fd.SlabOperator(sl, "laplacian", (4 * owned, 16, 16), torch.float32, accuracy=4, step_size=0.1, device=cpu)
+    # interior ranks only need 2P planes
+    fd.SlabOperator(fd.Slab(24, 1, 4), "laplacian", (24, 16, 16), torch.float32, accuracy=4, step_size=0.1, device=cpu)

@@ -194,3 +194,23 @@ def test_dense_matrix_is_the_operator():
     for method in O.METHODS:
         D = O.dense_matrix(31, accuracy=3, derivative=2, method=method, step_size=0.5)
         npt.assert_allclose(D @ x, O.difference(x, accuracy=3, derivative=2, method=method, step_size=0.5), rtol=1e-12, atol=1e-12)
+
+
+def test_torch_cpu_arm_equals_the_numpy_oracle():
+    """bench.py's CPU arm (oracle/fdx_oracle_torch.py, the reference graph on torch-CPU) against the NumPy oracle."""
+    import torch
+
+    from oracle import fdx_oracle_torch as OT
+
+    rng = np.random.default_rng(21)
+    for dtype, tol in ((np.float64, 1e-13), (np.float32, 2e-6)):
+        x = rng.standard_normal((20, 22, 24)).astype(dtype)
+        f = rng.standard_normal((3, 20, 22, 24)).astype(dtype)
+        kw = dict(accuracy=4, step_size=(0.1, 0.2, 0.3))
+        for name, arr, extra in (("laplacian", x, {}), ("gradient", x, {}), ("divergence", f, {"keepdims": False}), ("curl", f, {})):
+            ref = getattr(O, name)(arr, **kw, **extra)
+            got = getattr(OT, name)(torch.from_numpy(arr), **kw, **extra).numpy()
+            assert got.shape == ref.shape and got.dtype == ref.dtype
+            assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref)), name
+        d = OT.difference(torch.from_numpy(x), axis=1, accuracy=3, step_size=0.5, derivative=2, method="forward").numpy()
+        assert np.max(np.abs(d - O.difference(x, axis=1, accuracy=3, step_size=0.5, derivative=2, method="forward"))) <= tol * np.max(np.abs(d))

@@ -1,6 +1,6 @@
 """Round-robin timing of a fused operator under experiment switches (env), with SM clocks.
 
-    python tools/dbg_variants.py [op] [acc] [f32|f64] [n] -- "name:K=V,K=V" ...
+    python tools/time_variants.py [op] [acc] [f32|f64] [n] -- "name:K=V,K=V" ...
 Variants run interleaved for several rounds so that clock drift hits all of them alike; min and median are reported.
 """
 import os, sys, json, statistics
