@@ -54,6 +54,8 @@ class Slab(C.Structure):
         ("in_first", C.c_int32),
         ("in_planes", C.c_int32),
         ("out_first", C.c_int32),
+        ("z_begin2", C.c_int32),  # optional second range of output planes (the two shells of a slab in one launch)
+        ("z_end2", C.c_int32),
     ]
 
 
@@ -74,6 +76,7 @@ EXPORTS = (
     "fdx_error_string",
     "fdx_launch_count",
     "fdx_last_kernel",
+    "fdx_reload_env",
 )
 
 
@@ -108,6 +111,7 @@ def load():
         lib.fdx_error_string.argtypes = [i32]
         lib.fdx_launch_count.restype = i64
         lib.fdx_last_kernel.restype = C.c_char_p
+        lib.fdx_reload_env.restype = None
         for name in EXPORTS:
             getattr(lib, name)  # AttributeError here means header and library disagree
         _lib = lib
@@ -122,6 +126,11 @@ def check(code: int, what: str = "fdx call"):
 
 def launch_count() -> int:
     return int(load().fdx_launch_count())
+
+
+def reload_env() -> None:
+    """Make the library re-read the FDX_* switches (it snapshots them at first use)."""
+    load().fdx_reload_env()
 
 
 def last_kernel() -> str:
@@ -247,47 +256,46 @@ def _slab(slab):
     return C.byref(slab) if slab is not None else None
 
 
-_launch_memo: dict = {}
+class FusedLauncher:
+    """Everything a repeated fused launch needs, built once: entry point, plan-handle array, alpha array and two
+    reusable pointer arrays.  ``launch`` only writes the data pointers (computed from the base pointer and the
+    component stride: no tensor views) and fetches the raw current stream.  This is the host path of small grids
+    (BASELINE config 1: a 16 us kernel behind ~38 us of Python before)."""
 
+    __slots__ = ("kind", "plans", "keep", "hp", "al", "fn", "xin", "xout", "nin", "nout", "dev_index", "x_one", "o_one", "_xp", "_op")
 
-def _launch_args(kind: str, plans: Sequence[AxisPlan], alpha: Sequence[float], sfx: str, dev):
-    """Per-(operator, plans, alpha, dtype, device) constants of a fused launch: the entry point, the
-    plan-handle array and the alpha array (ctypes objects are built once, not per call)."""
-    key = (kind, tuple(id(p) for p in plans), tuple(alpha), sfx, dev.index)
-    hit = _launch_memo.get(key)
-    if hit is None or any(a is not b for a, b in zip(hit[0], plans)):
-        keep, hp = _handles(plans, dev)
-        hit = (tuple(plans), keep, hp, _alphas(alpha), getattr(load(), f"fdx_{kind}3d_{sfx}"))
-        if len(_launch_memo) > 512:
-            _launch_memo.clear()
-        _launch_memo[key] = hit
-    return hit
+    def __init__(self, kind: str, plans: Sequence[AxisPlan], alpha: Sequence[float], dtype: torch.dtype, device: torch.device):
+        if kind not in ("laplacian", "divergence", "gradient", "curl"):
+            raise ValueError(kind)
+        sfx = "f32" if dtype == torch.float32 else "f64"
+        self.kind, self.plans = kind, tuple(plans)
+        self.keep, self.hp = _handles(plans, device)
+        self.al = _alphas(alpha)
+        self.fn = getattr(load(), f"fdx_{kind}3d_{sfx}")
+        self.nin = 1 if kind in ("laplacian", "gradient") else 3
+        self.nout = 1 if kind in ("laplacian", "divergence") else 3
+        self.x_one, self.o_one = self.nin == 1, self.nout == 1
+        self.xin = None if self.x_one else (C.c_void_p * 3)()
+        self.xout = None if self.o_one else (C.c_void_p * 3)()
+        self.dev_index = device.index if device.index is not None else torch.cuda.current_device()
 
-
-def fused3d(kind: str, plans: Sequence[AxisPlan], xs, outs, alpha: Sequence[float], slab: "Slab | None" = None) -> int:
-    """Call one of the fused 3-D entry points.  ``xs`` / ``outs`` are a tensor (scalar field) or a
-    sequence of three tensors (vector field components).  Returns the library's status code for
-    FDX_EUNSUPPORTED so callers can fall back to ``axis_apply``; raises on any other error."""
-    x_one, o_one = isinstance(xs, torch.Tensor), isinstance(outs, torch.Tensor)
-    first = xs if x_one else xs[0]
-    dev = first.device
-    for t in ((xs,) if x_one else xs):
-        if not (t.is_cuda and t.is_contiguous()):
-            _require(t, "tensor")
-    for t in ((outs,) if o_one else outs):
-        if not (t.is_cuda and t.is_contiguous()):
-            _require(t, "tensor")
-    if kind not in ("laplacian", "divergence", "gradient", "curl"):
-        raise ValueError(kind)
-    _, _, hp, al, fn = _launch_args(kind, plans, alpha, _sfx(first), dev)
-    xin = C.c_void_p(xs.data_ptr()) if x_one else _ptrs(xs)
-    xout = C.c_void_p(outs.data_ptr()) if o_one else _ptrs(outs)
-    with _on_device(dev):
-        rc = fn(hp, xin, xout, al, _slab(slab), _stream_ptr(dev))
-    if rc == -2:  # FDX_EUNSUPPORTED
+    def launch(self, x_ptr: int, x_stride_bytes: int, out_ptr: int, out_stride_bytes: int) -> int:
+        """Enqueue on the current stream of the launcher's device (which must be the current device).  Returns the
+        library status: 0, or -2 when the fused kernels do not cover the call."""
+        if self.x_one:
+            xin = x_ptr
+        else:
+            xin = self.xin
+            xin[0], xin[1], xin[2] = x_ptr, x_ptr + x_stride_bytes, x_ptr + 2 * x_stride_bytes
+        if self.o_one:
+            xout = out_ptr
+        else:
+            xout = self.xout
+            xout[0], xout[1], xout[2] = out_ptr, out_ptr + out_stride_bytes, out_ptr + 2 * out_stride_bytes
+        rc = self.fn(self.hp, xin, xout, self.al, None, torch._C._cuda_getCurrentRawStream(self.dev_index))
+        if rc != 0 and rc != -2:
+            check(rc, f"fdx_{self.kind}3d")
         return rc
-    check(rc, f"fdx_{kind}3d")
-    return 0
 
 
 def fused3d_ptr(kind: str, plans: Sequence[AxisPlan], in_ptrs: Sequence[int], out_ptrs: Sequence[int], alpha: Sequence[float],
@@ -327,12 +335,12 @@ def fused3d_ptr(kind: str, plans: Sequence[AxisPlan], in_ptrs: Sequence[int], ou
 
 def prepare_fused3d_ptr(kind: str, plans: Sequence[AxisPlan], in_ptrs: Sequence[int], out_ptrs: Sequence[int], alpha: Sequence[float],
                         dtype: torch.dtype, device: torch.device, z_begin: int, z_end: int, in_first: int, in_planes: int,
-                        out_first: int):
+                        out_first: int, z_begin2: int = 0, z_end2: int = 0):
     """``fused3d_ptr`` with every ctypes object built once: returns ``launch(stream_ptr: int) -> None`` for callers
     that repeat the same slab call on fixed buffers (the multi-GPU step: three launches per 0.2 ms of GPU work)."""
     keep, hp = _handles(plans, device)
     sfx = "f32" if dtype == torch.float32 else "f64"
-    slab = Slab(int(z_begin), int(z_end), int(in_first), int(in_planes), int(out_first))
+    slab = Slab(int(z_begin), int(z_end), int(in_first), int(in_planes), int(out_first), int(z_begin2), int(z_end2))
     fn = getattr(load(), f"fdx_{kind}3d_{sfx}")
 
     def arr(ptrs):

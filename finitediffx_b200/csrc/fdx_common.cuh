@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/fdx_b200.h"
 
 // Device-resident plan (see include/fdx_b200.h :: fdx_axis_desc and finitediffx_b200/plan.py).
@@ -82,6 +84,16 @@ template <typename T, int V>
 __device__ __forceinline__ void st_vec(T* p, const Vec<T, V>& r) {
   *reinterpret_cast<Vec<T, V>*>(__builtin_assume_aligned(p, sizeof(T) * V)) = r;
 }
+
+// The FDX_* environment switches (experiments, bit-equality tests, timing tools) are read ONCE, when the library is
+// first used, into a snapshot; launches look them up there (usually an empty table) instead of calling getenv ~15
+// times per launch.  fdx_reload_env() takes a new snapshot (tests and tools that flip switches at run time).
+int env_int(const char* name, int dflt);
+const char* env_str(const char* name);  // nullptr when unset
+
+// Library epoch: bumped whenever a plan is destroyed (its address may be reused) or the switches are re-read; caches of
+// launch parameters keyed by plan pointers are valid for one epoch only.
+extern std::atomic<uint64_t> g_epoch;
 
 extern thread_local const char* g_last_kernel;
 void count_launch(const char* family, int launches = 1);

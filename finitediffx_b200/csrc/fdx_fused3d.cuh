@@ -28,6 +28,7 @@
 #include <cmath>
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <type_traits>
 
@@ -109,6 +110,8 @@ struct FusedParams {
   static constexpr int kXV = 16 / (int)sizeof(T), kXT = 2 * kXV + 1;
   int xfast, xnt_l, xnt_r;
   int plain_ok;  // interior CTAs may take the specialised (flag-free) march
+  int l2_ahead;   // planes the DRAM -> L2 prefetch runs ahead of the TMA loads (FDX_L2_AHEAD; 0 = none)
+  int issue_rot;  // the TMA issue duty rotates over the warps of the CTA (FDX_ISSUE_ROT=0 switches it off)
   int rim_first;  // launch order inside a chunk layer: rim tiles first (FDX_FUSED_RIMFIRST=0 switches it off)
   int dbg;       // experiments only (FDX_FUSED_DBG): 2 no x-band work, 16 every tile takes the interior copy (both: wrong results at the edges)
   int ydirect;   // ... and the tiles with y-band rows (the first / last tile row holds every band row and all of its taps)
@@ -294,6 +297,10 @@ __device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // Which field feeds the q-th y-derivative / x-derivative of the in-plane part
 //   LAP : ya0 = D1 x       xa0 = D2 x
 //   DIV : ya0 = D1 x1      xa0 = D2 x2
@@ -425,11 +432,23 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 #pragma unroll
     for (int f = 0; f < Tr::NIN; ++f)
       tma_load_3d_a(dst + G::field_off(f), &prm.tmap[f], bar_full + 8u * s, x0 - G::xoff(f), y0 - G::yoff(f), zt);
+    // DRAM -> L2 prefetch of a plane further ahead than the shared-memory ring reaches (prm.l2_ahead planes; 0 = off)
+    if (prm.l2_ahead > 0 && it + prm.l2_ahead < n_planes) {
+#pragma unroll
+      for (int f = 0; f < Tr::NIN; ++f)
+        tma_prefetch_3d(&prm.tmap[f], x0 - G::xoff(f), y0 - G::yoff(f), zt + prm.l2_ahead);
+    }
   };
   if (tid == 0) {
     for (int f = 0; f < Tr::NIN; ++f) asm volatile("prefetch.tensormap [%0];" ::"l"(&prm.tmap[f]) : "memory");
     for (int it = 0; it < LOOK && it < n_planes; ++it) issue(it);
   }
+  // The issue duty rotates over the warps (lane 0 of warp it % NW issues at step it): the ~35 instructions of an issue
+  // are then paid by every warp once in NW steps instead of by warp 0 at every step -- warp 0 was the slowest warp
+  // of an interior CTA and the step time of a CTA is that of its slowest warp.  (FDX_ISSUE_ROT=0: thread 0 always.)
+  constexpr int NW = G::NT / 32;
+  const bool rot = prm.issue_rot != 0;
+  auto issuer = [&](int it) { return rot ? (it % NW) * 32 : 0; };
 
   const int wrp = tid / 32;
   const int tx = (wrp % (CFG::TXV / LX)) * LX + lane % LX, ty = (wrp / (CFG::TXV / LX)) * TRW + lane / LX;
@@ -951,7 +970,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       const bool xe = be, ye = be;
       const bool inr = phase == 0 ? (it >= P && it < P + nout) : (phase == 2 || phase == 3);  // also an output plane of ours
       const bool emit = phase == 0 ? (it >= 2 * P) : (phase >= 3);  // output plane zc - P is complete after this step
-      if (tid == 0 && it + LOOK < n_planes) issue(it + LOOK);
+      if (tid == issuer(it) && it + LOOK < n_planes) issue(it + LOOK);
       mbar_wait_a(bar_full + 8u * stage, full_parity);
       VT zv[Tr::NACC][RY], tin[Tr::NACC][RY], eo[Tr::NACC][RY];
       if (inr) {
@@ -1024,7 +1043,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     const bool zb = fl & F_ZB;      // ... next to a physical z boundary
     const bool slow = fl & F_SLOW;  // the in-plane result needs the cold section
     const bool emit = fl & F_EMIT;  // output plane zc - P is complete after this step
-    if (tid == 0 && it + LOOK < n_planes) issue(it + LOOK);
+    if (tid == issuer(it) && it + LOOK < n_planes) issue(it + LOOK);
     mbar_wait_a(bar_full + 8u * stage, full_parity);
     fl_next = lds_flag(it + 1);  // (one byte past the last plane is still inside the flag area)
 
@@ -1136,34 +1155,26 @@ static int make_tmap(CUtensorMap* m, const T* base, int64_t n2, int64_t n1, int6
   return r == CUDA_SUCCESS ? FDX_OK : FDX_EUNSUPPORTED;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* s = std::getenv(name);
-  return s ? std::atoi(s) : dflt;
-}
+// (env_int / env_str: the library's snapshot of the FDX_* switches, fdx_common.cuh -- no getenv on the launch path)
 
 struct SlabArgs {
   int z_begin, z_end, in_first, in_planes, out_first;
+  int z_begin2, z_end2;  // optional second range of output planes (empty: z_begin2 == z_end2)
 };
 
 static SlabArgs slab_args(const fdx_plan_t plans[3], const fdx_slab* s) {
-  if (!s) return SlabArgs{0, plans[0]->n, 0, plans[0]->n, 0};
-  return SlabArgs{s->z_begin, s->z_end, s->in_first, s->in_planes, s->out_first};
+  if (!s) return SlabArgs{0, plans[0]->n, 0, plans[0]->n, 0, 0, 0};
+  return SlabArgs{s->z_begin, s->z_end, s->in_first, s->in_planes, s->out_first, s->z_begin2, s->z_end2 > s->z_begin2 ? s->z_end2 : s->z_begin2};
 }
 
+// Everything of a launch that does not depend on the data pointers: band tables, x-band layouts, tile counts, the
+// list of z chunks.  Cached per (plans, alpha, slab) by launch_cfg.  prm.n_chunks == 0 on return: nothing to do.
 template <Op OP, typename T, int P, typename CFG>
-static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const out[3], const double alpha[3],
-                      const SlabArgs& sl, cudaStream_t st) {
+static int build_params(FusedParams<T>& prm, const fdx_plan_t plans[3], const double alpha[3], const SlabArgs& sl) {
   using G = Geometry<OP, T, P, CFG>;
-  using Tr = OpTraits<OP>;
   const int n0 = plans[0]->n, n1 = plans[1]->n, n2 = plans[2]->n;
-  FusedParams<T> prm;
-  // plain loads/stores address planes by their global index through pointers to (virtual) plane 0;
-  // only addresses inside the caller's window are ever dereferenced.  TMA gets the real base.
-  const int64_t plane_elems = (int64_t)n1 * n2;
-  for (int f = 0; f < 3; ++f) {
-    prm.in[f] = f < Tr::NIN ? in[f] - (int64_t)sl.in_first * plane_elems : nullptr;
-    prm.out[f] = f < Tr::NOUT ? out[f] - (int64_t)sl.out_first * plane_elems : nullptr;
-  }
+  (void)n1;
+  prm.n_chunks = 0;
   int tab_used = 0, rows_used = 0;
   for (int k = 0; k < 3; ++k) {
     const fdx_plan_s* p = plans[k];
@@ -1224,6 +1235,8 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     if (env_int("FDX_XBAND_SLOW", 0)) ok = false;
     prm.xfast = ok ? 1 : 0, prm.xnt_l = ntl, prm.xnt_r = ntr;
     prm.plain_ok = env_int("FDX_FUSED_NOPLAIN", 0) ? 0 : 1;
+    prm.issue_rot = env_int("FDX_ISSUE_ROT", 1);
+    prm.l2_ahead = env_int("FDX_L2_AHEAD", 0);
     {
       const fdx_plan_s* py = plans[1];
       prm.ydirect = (py->nl <= G::TY && py->nr <= G::TY && py->wl <= G::TY + P && py->wr <= G::TY + P) ? 1 : 0;
@@ -1237,10 +1250,6 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
   prm.z_begin = sl.z_begin, prm.z_end = sl.z_end;
   prm.tz_off = -sl.in_first;
   prm.z_lo = 0, prm.z_hi = n0 - 1;
-  for (int f = 0; f < Tr::NIN; ++f) {
-    int rc = make_tmap<T>(&prm.tmap[f], in[f], n2, n1, (int64_t)sl.in_planes, G::box_x(f), G::box_y(f));
-    if (rc) return rc;
-  }
   prm.tiles_x = (n2 + G::TX - 1) / G::TX;
   prm.tiles_y = (n1 + G::TY - 1) / G::TY;
   {
@@ -1314,7 +1323,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
         sizes[n++] = sz, rem -= sz;
       }
     }
-    if (const char* cuts = std::getenv("FDX_FUSED_CUTS")) {  // experiments: explicit sizes, last z chunk first
+    if (const char* cuts = env_str("FDX_FUSED_CUTS")) {  // experiments: explicit sizes, last z chunk first
       n = 0, rem = nz;
       for (const char* c = cuts; *c && rem > 0 && n < kMaxCuts - 3;) {
         int v = std::atoi(c);
@@ -1345,11 +1354,78 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
       for (int i = n - 2; i >= 1; --i) prm.cut_z[k] = z, prm.cut_n[k] = (short)sizes[i], ++k, z += sizes[i];
     } else
     for (int i = n - 1; i >= 0; --i) prm.cut_z[k] = z, prm.cut_n[k] = (short)sizes[i], ++k, z += sizes[i];
+    // the optional second range: pieces of at most L planes behind the first range's chunks (any chunking gives the
+    // same bits; a piece that holds z-band planes takes the generic march)
+    for (int z2 = sl.z_begin2; z2 < sl.z_end2; z2 += L) {
+      if (k >= kMaxCuts) return FDX_EUNSUPPORTED;
+      prm.cut_z[k] = z2, prm.cut_n[k] = (short)std::min(L, sl.z_end2 - z2), ++k;
+    }
     if (k == 0) return FDX_OK;  // nothing to do
     prm.n_chunks = k;
   }
-  const int64_t blocks = tiles * prm.n_chunks;
-  if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
+  if (tiles * prm.n_chunks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
+  return FDX_OK;
+}
+
+template <Op OP, typename T, int P, typename CFG>
+static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const out[3], const double alpha[3],
+                      const SlabArgs& sl, cudaStream_t st) {
+  using G = Geometry<OP, T, P, CFG>;
+  using Tr = OpTraits<OP>;
+  const int n1 = plans[1]->n, n2 = plans[2]->n;
+  FusedParams<T> prm;
+  int rc;
+  {
+    // the pointer-independent part of the parameter block, cached (small grids are bound by the host launch path);
+    // an entry dies with the library epoch: any plan destroyed (its address may be reused) or the switches re-read
+    struct Entry {
+      uint64_t epoch;
+      const fdx_plan_s* p[3];
+      double a[3];
+      SlabArgs sl;
+      int rc;
+      FusedParams<T> prm;
+    };
+    constexpr int kEntries = 4;
+    static Entry cache[kEntries];
+    static int used = 0, next = 0;
+    static std::mutex mu;
+    const uint64_t epoch = g_epoch.load(std::memory_order_acquire);
+    std::lock_guard<std::mutex> lk(mu);
+    const Entry* hit = nullptr;
+    for (int i = 0; i < used && !hit; ++i) {
+      const Entry& e = cache[i];
+      if (e.epoch == epoch && e.p[0] == plans[0] && e.p[1] == plans[1] && e.p[2] == plans[2] && e.a[0] == alpha[0] && e.a[1] == alpha[1] &&
+          e.a[2] == alpha[2] && std::memcmp(&e.sl, &sl, sizeof(SlabArgs)) == 0)
+        hit = &e;
+    }
+    if (!hit) {
+      Entry& e = cache[next];
+      next = (next + 1) % kEntries;
+      if (used < kEntries) ++used;
+      e.epoch = epoch;
+      for (int k = 0; k < 3; ++k) e.p[k] = plans[k], e.a[k] = alpha[k];
+      e.sl = sl;
+      e.rc = build_params<OP, T, P, CFG>(e.prm, plans, alpha, sl);
+      hit = &e;
+    }
+    rc = hit->rc;
+    if (rc == FDX_OK) prm = hit->prm;
+  }
+  if (rc != FDX_OK) return rc;
+  if (prm.n_chunks == 0) return FDX_OK;  // nothing to do
+  // plain loads/stores address planes by their global index through pointers to (virtual) plane 0;
+  // only addresses inside the caller's window are ever dereferenced.  TMA gets the real base.
+  const int64_t plane_elems = (int64_t)n1 * n2;
+  for (int f = 0; f < 3; ++f) {
+    prm.in[f] = f < Tr::NIN ? in[f] - (int64_t)sl.in_first * plane_elems : nullptr;
+    prm.out[f] = f < Tr::NOUT ? out[f] - (int64_t)sl.out_first * plane_elems : nullptr;
+  }
+  for (int f = 0; f < Tr::NIN; ++f) {
+    int rc2 = make_tmap<T>(&prm.tmap[f], in[f], n2, n1, (int64_t)sl.in_planes, G::box_x(f), G::box_y(f));
+    if (rc2) return rc2;
+  }
+  const int64_t blocks = (int64_t)prm.tiles_x * prm.tiles_y * prm.n_chunks;
   auto kern = fused3d_kernel<OP, T, P, CFG>;
   {
     // once per kernel instantiation and device (the attribute is per device; 16 devices at most)
@@ -1386,48 +1462,19 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
 #endif
   if constexpr (sizeof(T) == FDX_SWEEP_TSIZE && P == FDX_SWEEP_P) {
     switch (cfg) {
-      FDX_CFG(1, 16, 16, 2, 4, 1)
-      FDX_CFG(2, 16, 16, 2, 4, 2)
-      FDX_CFG(3, 16, 16, 4, 3, 1)
-      FDX_CFG(4, 16, 32, 2, 4, 1)
-      FDX_CFG(5, 32, 8, 2, 4, 2)
-      FDX_CFG(6, 32, 8, 4, 3, 1)
-      FDX_CFG(7, 32, 16, 2, 3, 1)
-      FDX_CFG(8, 16, 16, 2, 6, 1)
-      FDX_CFG(9, 16, 8, 2, 4, 4)
-      FDX_CFG(10, 16, 8, 4, 4, 2)
-      FDX_CFG(11, 16, 8, 2, 4, 3)
-      FDX_CFG(12, 16, 16, 2, 6, 2)
-      FDX_CFG(13, 16, 8, 2, 6, 4)
-      FDX_CFG(14, 32, 8, 2, 6, 2)
-      FDX_CFG(15, 16, 8, 2, 8, 3)
-      FDX_CFG(16, 16, 8, 2, 6, 4)
-      FDX_CFG(17, 16, 16, 2, 4, 2)
-      FDX_CFG(18, 16, 16, 2, 8, 2)
-      FDX_CFG(19, 16, 8, 2, 5, 5)
-      FDX_CFG(20, 16, 8, 1, 8, 6)
-      FDX_CFG(21, 16, 16, 1, 6, 3)
-      FDX_CFG(22, 32, 8, 2, 4, 2)
-      FDX_CFG(23, 16, 8, 2, 8, 4)
-      FDX_CFG(24, 16, 8, 1, 8, 8)
-      FDX_CFG(25, 16, 8, 2, 8, 4, 8)
-      FDX_CFG(26, 16, 8, 2, 6, 4, 8)
-      FDX_CFG(27, 16, 8, 2, 8, 3, 8)
-      FDX_CFG(28, 16, 16, 2, 4, 2, 8)
-      FDX_CFG(29, 32, 8, 2, 4, 2, 8)
-      FDX_CFG(30, 16, 8, 2, 8, 4, 4)
-      FDX_CFG(31, 16, 32, 1, 4, 1)
-      FDX_CFG(32, 16, 16, 1, 4, 2)
-      FDX_CFG(33, 16, 16, 1, 6, 3)
-      FDX_CFG(34, 16, 8, 1, 8, 4)
-      FDX_CFG(35, 16, 8, 1, 8, 6)
-      FDX_CFG(36, 16, 16, 2, 4, 1)
-      FDX_CFG(37, 16, 8, 2, 4, 3)
-      FDX_CFG(38, 16, 8, 2, 6, 2)
-      FDX_CFG(39, 32, 8, 1, 4, 3)
-      FDX_CFG(40, 32, 8, 2, 4, 2)
-      FDX_CFG(41, 16, 8, 1, 8, 5, 8)
-      FDX_CFG(42, 16, 16, 1, 6, 3, 8)
+      // round-2 sweep list (tools/sweep_fused.py): Cfg<lanes x, thread rows, rows/thread, stages, min CTAs/SM, lanes x per warp>
+      FDX_CFG(1, 16, 8, 2, 8, 4, 8)    // the fp32 laplacian default: 64x16 tile, 128 threads
+      FDX_CFG(2, 16, 8, 2, 8, 4, 4)    // warps 4 lanes wide x 8 thread rows: the x-band work of an x-edge tile in ONE warp
+      FDX_CFG(3, 16, 8, 2, 8, 4, 16)   // full-width warps
+      FDX_CFG(4, 32, 4, 2, 8, 4, 8)    // 128x8 tile: half the TMA box rows per point
+      FDX_CFG(5, 32, 8, 2, 8, 2, 8)    // 128x16 tile, 256 threads
+      FDX_CFG(6, 16, 16, 2, 8, 2, 8)   // 64x32 tile, 256 threads
+      FDX_CFG(7, 16, 8, 2, 6, 4, 8)    // 6 stages
+      FDX_CFG(8, 8, 16, 2, 8, 4, 8)    // 32x32 tile
+      FDX_CFG(9, 16, 8, 2, 4, 3)       // the generic default
+      FDX_CFG(10, 16, 16, 1, 8, 4, 8)  // one row per thread, 256 threads, 64 registers
+      FDX_CFG(11, 32, 4, 2, 8, 4, 16)
+      FDX_CFG(12, 16, 4, 2, 8, 8, 8)   // 64x8 tile, 64 threads, 8 CTAs per SM
       default:
         break;
     }
@@ -1486,15 +1533,18 @@ static int fused_radius(const fdx_plan_t plans[3], const T* const in[3], T* cons
   for (int f = 0; f < Tr::NOUT; ++f)
     if (((uintptr_t)out[f] & 15) != 0) return 0;
   if (sl.z_begin < 0 || sl.z_end > plans[0]->n || sl.z_begin >= sl.z_end) return 0;
-  {
+  if (sl.z_end2 > sl.z_begin2 && (sl.z_begin2 < 0 || sl.z_end2 > plans[0]->n || (sl.z_begin2 < sl.z_end && sl.z_begin < sl.z_end2))) return -1;  // overlap
+  for (int r = 0; r < 2; ++r) {
     // the planes this call reads must lie inside the caller's window
+    const int zb = r ? sl.z_begin2 : sl.z_begin, ze = r ? sl.z_end2 : sl.z_end;
+    if (ze <= zb) continue;
     const fdx_plan_s* p0 = plans[0];
-    int lo = sl.z_begin - P < 0 ? 0 : sl.z_begin - P;
-    int hi = sl.z_end + P > p0->n ? p0->n : sl.z_end + P;
-    if (sl.z_begin < p0->nl) lo = 0, hi = hi > p0->wl ? hi : p0->wl;
-    if (sl.z_end > p0->n - p0->nr) lo = lo < p0->n - p0->wr ? lo : p0->n - p0->wr, hi = p0->n;
+    int lo = zb - P < 0 ? 0 : zb - P;
+    int hi = ze + P > p0->n ? p0->n : ze + P;
+    if (zb < p0->nl) lo = 0, hi = hi > p0->wl ? hi : p0->wl;
+    if (ze > p0->n - p0->nr) lo = lo < p0->n - p0->wr ? lo : p0->n - p0->wr, hi = p0->n;
     if (lo < sl.in_first || hi > sl.in_first + sl.in_planes) return -1;
-    if (sl.z_begin < sl.out_first) return -1;
+    if (zb < sl.out_first) return -1;
   }
   if (!encode_fn()) return 0;
   return P;
@@ -1576,7 +1626,7 @@ static int run(const fdx_plan_t plans[3], const T* const in[3], T* const out[3],
   }
   if (rc != FDX_EUNSUPPORTED) return rc;
   // fallback: only the whole-grid, no-halo form can be composed from the axis kernels
-  if (sl.z_begin != 0 || sl.z_end != plans[0]->n || sl.in_first != 0 || sl.out_first != 0) return FDX_EUNSUPPORTED;
+  if (sl.z_begin != 0 || sl.z_end != plans[0]->n || sl.in_first != 0 || sl.out_first != 0 || sl.z_end2 > sl.z_begin2) return FDX_EUNSUPPORTED;
   return composed<OP, T>(plans, in, out, alpha, stream);
 }
 

@@ -4,19 +4,71 @@
 // only cache -- the jax.jit cache around the coefficient solve, finitediffx/_src/utils.py:100 --
 // except that the coefficients arrive already solved (exactly, in float64) from the host.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <new>
+#include <string>
+#include <utility>
+#include <vector>
+
+extern char** environ;
 
 #include "fdx_common.cuh"
 
 namespace fdx {
 thread_local const char* g_last_kernel = "";
+std::atomic<uint64_t> g_epoch{1};
 static std::atomic<int64_t> g_launches{0};
 void count_launch(const char* family, int launches) {
   g_last_kernel = family;
   g_launches.fetch_add(launches, std::memory_order_relaxed);
 }
+
+// ---- snapshot of the FDX_* environment switches
+using EnvTable = std::vector<std::pair<std::string, std::string>>;
+static std::mutex g_env_mu;
+static const EnvTable* snapshot_env() {
+  auto* t = new EnvTable();
+  for (char** e = environ; e && *e; ++e) {
+    if (std::strncmp(*e, "FDX_", 4) != 0) continue;
+    const char* eq = std::strchr(*e, '=');
+    if (eq) t->emplace_back(std::string(*e, eq - *e), std::string(eq + 1));
+  }
+  return t;
+}
+static std::atomic<const EnvTable*> g_env_cur{nullptr};
+static const EnvTable& env_table() {
+  const EnvTable* t = g_env_cur.load(std::memory_order_acquire);
+  if (!t) {
+    std::lock_guard<std::mutex> lk(g_env_mu);
+    t = g_env_cur.load(std::memory_order_acquire);
+    if (!t) {
+      t = snapshot_env();
+      g_env_cur.store(t, std::memory_order_release);
+    }
+  }
+  return *t;
+}
+const char* env_str(const char* name) {
+  for (const auto& kv : env_table())
+    if (kv.first == name) return kv.second.c_str();
+  return nullptr;
+}
+int env_int(const char* name, int dflt) {
+  const char* s = env_str(name);
+  return s ? std::atoi(s) : dflt;
+}
 }  // namespace fdx
+
+// Re-read the FDX_* switches (they are snapshotted at first use).  Not for concurrent use with launches that are
+// reading an older snapshot's strings: tests and timing tools call it between launches.
+extern "C" void fdx_reload_env(void) {
+  std::lock_guard<std::mutex> lk(fdx::g_env_mu);
+  fdx::g_env_cur.store(fdx::snapshot_env(), std::memory_order_release);  // the old table is leaked (a few bytes per call)
+  fdx::g_epoch.fetch_add(1, std::memory_order_acq_rel);
+}
 
 extern "C" int fdx_plan_create(fdx_plan_t* plan, const fdx_axis_desc* d) {
   if (!plan || !d) return FDX_EINVAL;
@@ -69,6 +121,7 @@ extern "C" int fdx_plan_create(fdx_plan_t* plan, const fdx_axis_desc* d) {
 
 extern "C" int fdx_plan_destroy(fdx_plan_t plan) {
   if (!plan) return FDX_OK;
+  fdx::g_epoch.fetch_add(1, std::memory_order_acq_rel);
   cudaFree(plan->band_l);
   cudaFree(plan->band_r);
   delete[] plan->h_band_l;

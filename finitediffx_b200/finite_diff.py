@@ -94,21 +94,29 @@ _fused_memo: dict = {}
 _plan_mod._dependent_caches.append(_fused_memo.clear)
 
 
-def _fused_lookup(terms, n_in: int, n_out: int, spatial):
-    """Memoised recognition of a term list as a fused 3-D operator: (kind, plans, alpha) or None."""
-    key = (terms, n_in, n_out, spatial)
-    hit = _fused_memo.get(key, False)
-    if hit is False:
+def _fused_lookup(terms, n_in: int, n_out: int, spatial, dtype, device):
+    """Memoised recognition of a term list as a fused 3-D operator: a prepared ``_cabi.FusedLauncher`` or None.
+    The key uses the identity of the term tuple (``_memo_terms`` hands out the same tuple for repeated calls, and the
+    entry keeps it alive), so a hit costs one small-tuple hash instead of hashing every Term."""
+    key = (id(terms), n_in, n_out, spatial, dtype, device.index)
+    hit = _fused_memo.get(key)
+    if hit is not None and hit[0] is terms:
+        return hit[1]
+    vkey = (terms, n_in, n_out, spatial, dtype, device.index)  # an equal term list built anew (tensor arguments)
+    hit = _fused_memo.get(vkey)
+    if hit is not None:
+        launcher = hit[1]
+    else:
         m = _match_fused(terms, n_in, n_out, spatial)
-        if m is None:
-            hit = None
-        else:
+        launcher = None
+        if m is not None:
             kind, axis_terms = m
-            hit = (kind, tuple(t.plan(spatial[k]) for k, t in enumerate(axis_terms)), tuple(t.alpha for t in axis_terms))
-        if len(_fused_memo) > 256:
+            launcher = _cabi.FusedLauncher(kind, tuple(t.plan(spatial[k]) for k, t in enumerate(axis_terms)), tuple(t.alpha for t in axis_terms), dtype, device)
+        if len(_fused_memo) > 512:
             _fused_memo.clear()
-        _fused_memo[key] = hit
-    return hit
+        _fused_memo[vkey] = (terms, launcher)
+    _fused_memo[key] = (terms, launcher)
+    return launcher
 
 
 def _execute(terms: Sequence[Term], x: torch.Tensor, n_out: int) -> torch.Tensor:
@@ -117,13 +125,13 @@ def _execute(terms: Sequence[Term], x: torch.Tensor, n_out: int) -> torch.Tensor
     out = torch.empty((n_out,) + spatial, dtype=x.dtype, device=x.device)
     if x.numel() == 0:
         return out
-    fused = _fused_lookup(terms, n_in, n_out, spatial)
-    if fused is not None:
-        kind, plans, alpha = fused
-        xs = x[0] if kind in ("laplacian", "gradient") else [x[0], x[1], x[2]]
-        outs = out[0] if kind in ("laplacian", "divergence") else [out[0], out[1], out[2]]
-        if _cabi.fused3d(kind, plans, xs, outs, alpha) == 0:
-            if n_out > 3 and kind == "gradient":
+    launcher = _fused_lookup(terms, n_in, n_out, spatial, x.dtype, x.device) if len(spatial) == 3 else None
+    if launcher is not None:
+        esz = x.element_size()
+        with _cabi._on_device(x.device):
+            rc = launcher.launch(x.data_ptr(), x.stride(0) * esz, out.data_ptr(), out.stride(0) * esz)
+        if rc == 0:
+            if n_out > 3 and launcher.kind == "gradient":
                 out[3:].zero_()
             return out
     written = [False] * n_out
@@ -134,6 +142,20 @@ def _execute(terms: Sequence[Term], x: torch.Tensor, n_out: int) -> torch.Tensor
         if not w:
             out[co].zero_()
     return out
+
+
+_transposed_memo: dict = {}
+_plan_mod._dependent_caches.append(_transposed_memo.clear)
+
+
+def _transposed(terms: tuple) -> tuple:
+    """The transposed term list, one tuple object per forward list (so the launch caches hit on its identity)."""
+    hit = _transposed_memo.get(id(terms))
+    if hit is None or hit[0] is not terms:
+        if len(_transposed_memo) > 256:
+            _transposed_memo.clear()
+        hit = _transposed_memo[id(terms)] = (terms, tuple(t.t() for t in terms))
+    return hit[1]
 
 
 class _StencilOp(torch.autograd.Function):
@@ -147,13 +169,19 @@ class _StencilOp(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         g = g.contiguous()
-        terms_t = tuple(t.t() for t in ctx.terms)
-        return _StencilOp.apply(g, terms_t, ctx.n_in), None, None
+        return _StencilOp.apply(g, _transposed(ctx.terms), ctx.n_in), None, None
 
 
 # ------------------------------------------------------------------------ array marshalling
+def _identity(r):
+    return r
+
+
 def _to_device(array):
     """-> (contiguous CUDA tensor of float32/float64, restore(result) -> caller's array kind)."""
+    if type(array) is torch.Tensor and array.is_cuda and (array.dtype is torch.float32 or array.dtype is torch.float64) and array.is_contiguous():
+        _cabi.load()
+        return array, _identity  # the common case: nothing to convert, nothing to restore
     if isinstance(array, torch.Tensor):
         t, kind = array, ("cuda" if array.is_cuda else "cpu")
     else:
@@ -191,8 +219,6 @@ def _host_streamed(kind: str, array, accuracy, step_size, method: str, n_out: in
     """Large host-resident 3-D grids: pipeline slabs through the GPU (H2D, kernel, D2H overlapped,
     finitediffx_b200/slab.py) instead of staging the whole array in HBM.  Returns None when the
     call is not of that kind, so that the caller takes the ordinary path."""
-    from . import slab as _slab
-
     if isinstance(array, torch.Tensor):
         if array.is_cuda or array.requires_grad:
             return None
@@ -201,6 +227,8 @@ def _host_streamed(kind: str, array, accuracy, step_size, method: str, n_out: in
         t, as_numpy = torch.from_numpy(np.ascontiguousarray(array)), True
     else:
         return None
+    from . import slab as _slab
+
     nin = _slab.FIELDS[kind][0]
     if t.dtype not in (torch.float32, torch.float64) or not torch.cuda.is_available():
         return None
@@ -252,10 +280,20 @@ def _norm_axis(axis: int, ndim: int) -> int:
     return axis % ndim
 
 
+_validated: dict = {}
+_plan_mod._dependent_caches.append(_validated.clear)
+
+
 def _run(x_fields: torch.Tensor, terms, n_out: int) -> torch.Tensor:
-    terms = tuple(terms)
-    for t in terms:  # validate sizes/methods up front so errors match the reference's ValueError
-        t.plan(x_fields.shape[1 + t.axis])
+    if type(terms) is not tuple:
+        terms = tuple(terms)
+    vkey = (id(terms), x_fields.shape)
+    if _validated.get(vkey) is not terms:
+        for t in terms:  # validate sizes/methods up front so errors match the reference's ValueError
+            t.plan(x_fields.shape[1 + t.axis])
+        if len(_validated) > 256:
+            _validated.clear()
+        _validated[vkey] = terms  # (keeps the tuple alive, so its id cannot be reused by another term list)
     if not x_fields.requires_grad or not torch.is_grad_enabled():
         return _execute(terms, x_fields, n_out)  # skip the autograd.Function round trip
     return _StencilOp.apply(x_fields, terms, n_out)

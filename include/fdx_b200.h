@@ -83,11 +83,15 @@ int fdx_axis_apply_f64(fdx_plan_t plan, const double* x, double* out, int64_t ou
  *                        clipped to the grid (P = stencil radius) and, when the range touches a
  *                        physical boundary, the planes under the one-sided boundary stencils;
  *                        all of them must lie inside the window (FDX_EINVAL otherwise);
- *   out_first          : every OUTPUT pointer designates global plane out_first.               */
+ *   out_first          : every OUTPUT pointer designates global plane out_first;
+ *   z_begin2,z_end2    : an optional second, disjoint range of output planes served by the same launch.        */
 typedef struct {
   int32_t z_begin, z_end;
   int32_t in_first, in_planes;
   int32_t out_first;
+  /* optional SECOND range of output planes in the same launch (z_begin2 == z_end2: none), disjoint from the
+   * first: the two P-plane shells of a slab next to its two cuts go out as ONE launch behind the halo exchange */
+  int32_t z_begin2, z_end2;
 } fdx_slab;
 
 /* laplacian (finite_diff.py:532-575):  out = sum_k alpha[k] * D_k x                         */
@@ -126,6 +130,10 @@ const char* fdx_error_string(int code); /* static string for FDX_E* and cudaErro
 int64_t fdx_launch_count(void);
 /* name of the kernel family the last call on this thread dispatched to ("axis_stream", ...) */
 const char* fdx_last_kernel(void);
+
+/* The FDX_* environment switches of the fused kernels (experiments, bit-equality tests) are snapshotted when the
+ * library is first used; this takes a new snapshot.  Test / tooling hook, not part of the hot path. */
+void fdx_reload_env(void);
 
 #ifdef __cplusplus
 }

@@ -261,12 +261,9 @@ def test_fused_kernels_cover_forward_and_adjoint():
             g = torch.randn_like(out)
             (gx,) = torch.autograd.grad(out, arg, g)
             fused_bwd = _cabi.last_kernel()
-            os.environ["FDX_FUSED_DISABLE"] = "1"
-            try:
+            with _env(FDX_FUSED_DISABLE=1):
                 out2 = getattr(fdx, name)(arg, accuracy=acc, step_size=0.1, **kw)
                 (gx2,) = torch.autograd.grad(out2, arg, g)
-            finally:
-                os.environ["FDX_FUSED_DISABLE"] = "0"
             tol = 2e-5
             assert ((out - out2).abs().max() / out2.abs().max()).item() < tol, (name, acc)
             assert ((gx - gx2).abs().max() / gx2.abs().max()).item() < tol, (name, acc)
@@ -368,6 +365,7 @@ def _env(**kw):
     def cm():
         old = {k: os.environ.get(k) for k in kw}
         os.environ.update({k: str(v) for k, v in kw.items()})
+        _cabi.reload_env()  # the library snapshots the FDX_* switches
         try:
             yield
         finally:
@@ -376,6 +374,7 @@ def _env(**kw):
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
+            _cabi.reload_env()
 
     return cm()
 

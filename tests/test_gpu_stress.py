@@ -46,14 +46,17 @@ def test_random_shapes_fused_vs_axis_kernels(seed):
         old = os.environ.get("FDX_FUSED_DISABLE")
         try:
             os.environ["FDX_FUSED_DISABLE"] = "0"
+            _cabi.reload_env()  # the library snapshots the FDX_* switches
             out, ga, k = run()
             os.environ["FDX_FUSED_DISABLE"] = "1"
+            _cabi.reload_env()
             out_r, ga_r, _ = run()
         finally:
             if old is None:
                 os.environ.pop("FDX_FUSED_DISABLE", None)
             else:
                 os.environ["FDX_FUSED_DISABLE"] = old
+            _cabi.reload_env()
         tol = 3e-5 if dtype == torch.float32 else 2e-11
         e1 = ((out - out_r).abs().max() / out_r.abs().max()).item()
         e2 = ((ga - ga_r).abs().max() / ga_r.abs().max()).item()

@@ -46,10 +46,13 @@ for case in range(cases):
         return out.detach(), ga, k, _cabi.last_kernel()
 
     os.environ["FDX_FUSED_DISABLE"] = "0"
+    __import__("finitediffx_b200._cabi", fromlist=["reload_env"]).reload_env()  # the library snapshots the FDX_* switches
     out, ga, k1, k2 = run()
     os.environ["FDX_FUSED_DISABLE"] = "1"
+    __import__("finitediffx_b200._cabi", fromlist=["reload_env"]).reload_env()  # the library snapshots the FDX_* switches
     out_r, ga_r, _, _ = run()
     os.environ["FDX_FUSED_DISABLE"] = "0"
+    __import__("finitediffx_b200._cabi", fromlist=["reload_env"]).reload_env()  # the library snapshots the FDX_* switches
     tol = 3e-5 if dtype == torch.float32 else 2e-11
     e1 = ((out - out_r).abs().max() / out_r.abs().max()).item()
     e2 = ((ga - ga_r).abs().max() / ga_r.abs().max()).item()

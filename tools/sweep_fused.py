@@ -37,18 +37,23 @@ def call(x):
 
 
 os.environ["FDX_FUSED_DISABLE"] = "1"
+__import__("finitediffx_b200._cabi", fromlist=["reload_env"]).reload_env()  # the library snapshots the FDX_* switches
 ref = call(xs[0])
 torch.cuda.synchronize()
 ref_kernel = _cabi.last_kernel()
 os.environ["FDX_FUSED_DISABLE"] = "0"
+__import__("finitediffx_b200._cabi", fromlist=["reload_env"]).reload_env()  # the library snapshots the FDX_* switches
 scale = ref.abs().max().item()
 bytes_pp = (fields_in + fields_out) * xs[0].element_size()
 results = []
 for cfg in cfgs:
     for chunk in chunks:
         os.environ["FDX_FUSED_CFG"] = str(cfg)
+        __import__("finitediffx_b200._cabi", fromlist=["reload_env"]).reload_env()  # the library snapshots the FDX_* switches
         os.environ["FDX_FUSED_CHUNK"] = str(chunk).split(":")[0]
+        __import__("finitediffx_b200._cabi", fromlist=["reload_env"]).reload_env()  # the library snapshots the FDX_* switches
         os.environ["FDX_FUSED_CHUNK_SHORT"] = str(chunk).split(":")[1] if ":" in str(chunk) else "0"
+        __import__("finitediffx_b200._cabi", fromlist=["reload_env"]).reload_env()  # the library snapshots the FDX_* switches
         try:
             out = call(xs[0])
             torch.cuda.synchronize()

@@ -8,6 +8,7 @@ os.environ["FDX_FUSED_EXPERIMENTS"] = "1"  # lets FDX_FUSED_DBG through (timing 
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import finitediffx_b200 as fdx
+from finitediffx_b200 import _cabi
 try:
     import pynvml
     pynvml.nvmlInit()
@@ -61,6 +62,7 @@ for rnd in range(rounds):
         for k in keys:
             os.environ.pop(k, None)
         os.environ.update(env)
+        _cabi.reload_env()  # the library snapshots the FDX_* switches
         for i in range(3):
             call(xs[i % 3])
         torch.cuda.synchronize()
