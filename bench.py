@@ -355,9 +355,13 @@ def run_ours(args):
         fn(inputs[i % len(inputs)])
     torch.cuda.synchronize()
     graphed = False
-    if world > 1 and os.environ.get("FDX_BENCH_GRAPH", "0") == "1":  # opt-in
-        # multi-GPU steps are host-bound (NCCL group + events + three launches per 0.2 ms of GPU work): capture
-        # one step per rotating buffer in a CUDA graph and replay it (same kernels, same exchange, same buffers)
+    halo_mode = op.mode if world > 1 or strong else None
+    want_graph = os.environ.get("FDX_BENCH_GRAPH", "1" if halo_mode == "peer" else "0") == "1"
+    if world > 1 and want_graph:
+        # a multi-GPU step is a dozen enqueue calls (barriers, peer copies, events, two launches) for 0.2 ms of GPU work:
+        # one step per rotating buffer is captured in a CUDA graph and replayed (same kernels, exchange and buffers).
+        # Default with peer-memory halos (nothing but memcpys and kernels in the graph); opt-in with NCCL halos
+        # (FDX_BENCH_GRAPH=1: tearing the process group down after an NCCL capture hung on this stack).
         for b in inputs:
             op.capture(b)
         fn = lambda b: op.replay(b)
@@ -409,7 +413,8 @@ def run_ours(args):
     if not args.no_extras and args.workload == HEADLINE:
         del inputs
         if world > 1:
-            del op
+            op.release_graphs()
+            del op, fn
         torch.cuda.empty_cache()
         try:
             extras = _extras_single(fdx, _cabi, dev, peak) if world == 1 else _extras_multi(world, rank, dev, dist, peak)
@@ -418,7 +423,7 @@ def run_ours(args):
 
     if rank != 0:
         if dist:
-            dist.destroy_process_group()
+            _teardown(dist, graphed and halo_mode != "peer")
         return 0
 
     alg_bytes = _bytes_per_point(w) * pts_per_gpu
@@ -447,6 +452,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": config,
         "graph_replay": graphed,
+        "halo_transport": halo_mode,
         "clocks": sampler.summary() if sampler else None,
         "e2e": e2e,
         "gpu_launches": int(launches),
@@ -470,14 +476,20 @@ def run_ours(args):
         line["extras"] = extras
     print(json.dumps(line), flush=True)
     if dist:
-        if graphed:
-            # (opt-in mode) tearing the process group down with captured NCCL work hung on this stack
-            # (torch 2.11 / NCCL 2.28.9): leave without the teardown
-            torch.cuda.synchronize()
-            sys.stdout.flush()
-            os._exit(0)
-        dist.destroy_process_group()
+        _teardown(dist, graphed and halo_mode != "peer")
     return 0
+
+
+def _teardown(dist, nccl_captured):
+    import torch
+
+    torch.cuda.synchronize()
+    if nccl_captured:
+        # (opt-in mode) tearing the process group down with captured NCCL work hung on this stack
+        # (torch 2.11 / NCCL 2.28.9): leave without the teardown
+        sys.stdout.flush()
+        os._exit(0)
+    dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------ extras: every BASELINE config
@@ -607,16 +619,22 @@ def _extras_multi(world, rank, dev, dist, peak):
         slab = fd.Slab(global_n0=n, rank=rank, world=world, group=dist.group.WORLD)
         op = fd.SlabOperator(slab, w["op"], spatial=(n, n, n), dtype=dt, accuracy=w["accuracy"], step_size=1.0 / (n - 1), device=dev, n_buffers=1)
         op.fill_random(0, seed=100 * rank)
-        secs = _time_device(lambda b: op.step(b), [0], 10, 3, barrier=lambda: dist.barrier())
+        step = lambda b: op.step(b)
+        if op.mode == "peer" and os.environ.get("FDX_BENCH_GRAPH", "1") == "1":
+            op.step(0)
+            op.capture(0)
+            step = lambda b: op.replay(b)
+        secs = _time_device(step, [0], 10, 3, barrier=lambda: dist.barrier())
         t = torch.tensor([secs], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_s = float(t.item()) / 10
         alone = _time_device(lambda b: op.step_alone(b), [0], 10, 3) / 10
         dist.barrier()
         e = _entry(n**3, _bytes_per_point(w), step_s, peak * world, n_gpus=world, slab_alone_ms=alone * 1e3, overlap_efficiency=alone / step_s,
-                   halo_bytes_per_step_per_rank=int(op.halo_bytes_per_step))
+                   halo_bytes_per_step_per_rank=int(op.halo_bytes_per_step), halo_transport=op.mode)
         ex[name] = e
-        del op
+        op.release_graphs()
+        del op, step
         torch.cuda.empty_cache()
     return ex
 

@@ -75,11 +75,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 }
 
 // ------------------------------------------------------------------------------ parameters
-constexpr int kTabMax = 640;   // band coefficients of all 6 sides, carried in the parameter block
-constexpr int kRowsMax = 96;   // band rows of all 6 sides
+// Band tables, sized by the stencil radius so that TRANSPOSED plans stay fused at every accuracy the forward kernels
+// cover (the adjoint's bands are P + L rows of up to 2L + 1 taps: 6 sides x 18 x 24 at P = 6).  Radius <= 3 keeps the
+// small block (the latency-bound small grids of BASELINE config 1 pay for the size of the parameter block).
+__host__ __device__ constexpr int tab_max(int P) { return P <= 3 ? 640 : (P == 4 ? 1280 : (P == 5 ? 1920 : 2688)); }  // band coefficients of all 6 sides
+__host__ __device__ constexpr int xtab_max(int P) { return P <= 3 ? 320 : (P == 4 ? 384 : (P == 5 ? 640 : 896)); }    // x-band coefficients of both sides (staged in shared memory by the x-edge CTAs)
+constexpr int kRowsMax = 128;  // band rows of all 6 sides
 constexpr int kMaxPlanes = 383;  // planes one CTA may march through (per-plane flag bytes in shared memory)
 constexpr int kMaxCuts = 128;    // z chunks per launch
-constexpr int kXTabMax = 320;    // x-band coefficients of both sides, staged in shared memory by the x-edge CTAs
 
 template <typename T>
 struct AxisDev {
@@ -90,7 +93,7 @@ struct AxisDev {
   T c[FDX_MAX_TAPS];  // main taps, pre-multiplied by alpha
 };
 
-template <typename T>
+template <typename T, int P_>
 struct FusedParams {
   CUtensorMap tmap[3];  // one per input field
   const T* in[3];       // logical plane 0 of each input field (band gathers)
@@ -118,7 +121,7 @@ struct FusedParams {
   int xdirect;   // ... and so may the tiles with x-band columns (the owner's window holds all band taps)
   T xcl[kXT][kXV], xcr[kXT][kXV];
   short2 rng[kRowsMax];  // [first, last+1) nonzero band column of every band row
-  T tab[kTabMax];
+  T tab[tab_max(P_)];
 };
 
 // TXV x TYT threads own RY rows x one 16-byte vector each; a warp covers LX x (32 / LX) of them.  A narrow
@@ -178,7 +181,7 @@ struct Geometry {
     for (int f = 0; f < Tr::NIN; ++f) b += box_x(f) * box_y(f) * (int)sizeof(T);
     return b;
   }
-  static constexpr int XTAB_BYTES = ((kXTabMax * (int)sizeof(T) + 127) / 128) * 128;
+  static constexpr int XTAB_BYTES = ((xtab_max(P) * (int)sizeof(T) + 127) / 128) * 128;
   // barriers (128 B) + plane flags (384 B) + x-band table + alignment slack + stage ring
   static constexpr int SMEM_BYTES = 512 + XTAB_BYTES + 128 + CFG::STAGES * STAGE_BYTES;
 };
@@ -321,7 +324,7 @@ __host__ __device__ constexpr int out_lag(int o) {
 
 template <Op OP, typename T, int P, typename CFG>
 __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
-    fused3d_kernel(const __grid_constant__ FusedParams<T> prm) {
+    fused3d_kernel(const __grid_constant__ FusedParams<T, P> prm) {
   using G = Geometry<OP, T, P, CFG>;
   using Tr = OpTraits<OP>;
   using IP = InPlane<OP>;
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(flag_base + (uint32_t)i), "r"(f) : "memory");
   }
   if (xedge_l || xedge_r) {  // the dense x-band rows (left, then right) go to shared memory
-    const int cnt = prm.ax[2].nl * prm.ax[2].wl + prm.ax[2].nr * prm.ax[2].wr;  // <= kXTabMax, host-checked
+    const int cnt = prm.ax[2].nl * prm.ax[2].wl + prm.ax[2].nr * prm.ax[2].wr;  // <= xtab_max(P), host-checked
     for (int i = tid; i < cnt; i += G::NT) {
       const T c = prm.tab[prm.ax[2].tab_l + i];
       if constexpr (sizeof(T) == 4)
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       }
     }
     if (xb) {
-      constexpr int XT = FusedParams<T>::kXT;
+      constexpr int XT = FusedParams<T, P>::kXT;
       if (own_l) {
         T val[V];
 #pragma unroll
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // back with shuffles, so a warp pays for one row, not RY.
   const bool xfast = prm.xfast != 0;
   auto xband_fast = [&](uint32_t row /* shared address of this thread's vector in the row of yg */, int pitch, VT (&xs)[RY]) {
-    constexpr int XT = FusedParams<T>::kXT;
+    constexpr int XT = FusedParams<T, P>::kXT;
 #pragma unroll
     for (int side = 0; side < 2; ++side) {
       if (!(side ? xedge_r : xedge_l)) continue;  // CTA-uniform
@@ -1170,7 +1173,7 @@ static SlabArgs slab_args(const fdx_plan_t plans[3], const fdx_slab* s) {
 // Everything of a launch that does not depend on the data pointers: band tables, x-band layouts, tile counts, the
 // list of z chunks.  Cached per (plans, alpha, slab) by launch_cfg.  prm.n_chunks == 0 on return: nothing to do.
 template <Op OP, typename T, int P, typename CFG>
-static int build_params(FusedParams<T>& prm, const fdx_plan_t plans[3], const double alpha[3], const SlabArgs& sl) {
+static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans[3], const double alpha[3], const SlabArgs& sl) {
   using G = Geometry<OP, T, P, CFG>;
   const int n0 = plans[0]->n, n1 = plans[1]->n, n2 = plans[2]->n;
   (void)n1;
@@ -1181,11 +1184,14 @@ static int build_params(FusedParams<T>& prm, const fdx_plan_t plans[3], const do
     AxisDev<T>& a = prm.ax[k];
     a.n = p->n, a.nl = p->nl, a.wl = p->wl, a.nr = p->nr, a.wr = p->wr;
     a.alpha = (T)alpha[k];
-    for (int t = 0; t < FDX_MAX_TAPS; ++t) a.c[t] = t < 2 * P + 1 ? (T)(p->main_taps[t] * alpha[k]) : (T)0;
+    for (int t = 0; t < FDX_MAX_TAPS; ++t) {  // tap t of the kernel sits at offset t - P; the plan's taps cover lo .. hi
+      const int o = t - P;
+      a.c[t] = (t < 2 * P + 1 && o >= p->lo && o <= p->hi) ? (T)(p->main_taps[o - p->lo] * alpha[k]) : (T)0;
+    }
     for (int side = 0; side < 2; ++side) {
       const int rows = side ? p->nr : p->nl, w = side ? p->wr : p->wl;
       const double* h = side ? p->h_band_r : p->h_band_l;
-      if (tab_used + rows * w > kTabMax || rows_used + rows > kRowsMax) return FDX_EUNSUPPORTED;
+      if (tab_used + rows * w > tab_max(P) || rows_used + rows > kRowsMax) return FDX_EUNSUPPORTED;
       (side ? a.tab_r : a.tab_l) = tab_used;
       (side ? a.rng_r : a.rng_l) = rows_used;
       for (int r = 0; r < rows; ++r) {
@@ -1206,7 +1212,7 @@ static int build_params(FusedParams<T>& prm, const fdx_plan_t plans[3], const do
   }
   {
     // fast x bands: rows in one vector, row r's taps inside columns [r, r + nt)
-    constexpr int XV = FusedParams<T>::kXV, XT = FusedParams<T>::kXT;
+    constexpr int XV = FusedParams<T, P>::kXV, XT = FusedParams<T, P>::kXT;
     const fdx_plan_s* px = plans[2];
     const int ntl = px->wl - px->nl + 1, ntr = px->wr - px->nr + 1;
     bool ok = px->nl <= XV && px->nr <= XV && ntl >= 1 && ntr >= 1 && ntl <= XT && ntr <= XT && n2 >= 3 * XV;
@@ -1258,7 +1264,7 @@ static int build_params(FusedParams<T>& prm, const fdx_plan_t plans[3], const do
     const fdx_plan_s* px = plans[2];
     const int xl = n2 > G::TX ? n2 - G::TX : 0;  // origin of the (shifted) last tile
     if (px->nl > G::TX || px->wl > G::TX + G::HX || n2 - xl < px->nr || xl > n2 - px->wr + G::HX) return FDX_EUNSUPPORTED;
-    if (px->nl * px->wl + px->nr * px->wr > kXTabMax) return FDX_EUNSUPPORTED;
+    if (px->nl * px->wl + px->nr * px->wr > xtab_max(P)) return FDX_EUNSUPPORTED;
     if (prm.tiles_x == 2) {  // the cut between the first tile and the shifted second one (see the kernel): the right band
       const int cut = std::min(G::TX, std::max(xl, ((px->nl + G::V - 1) / G::V) * G::V));  // must lie behind it
       if (n2 - px->nr < cut) return FDX_EUNSUPPORTED;
@@ -1373,7 +1379,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
   using G = Geometry<OP, T, P, CFG>;
   using Tr = OpTraits<OP>;
   const int n1 = plans[1]->n, n2 = plans[2]->n;
-  FusedParams<T> prm;
+  FusedParams<T, P> prm;
   int rc;
   {
     // the pointer-independent part of the parameter block, cached (small grids are bound by the host launch path);
@@ -1384,7 +1390,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
       double a[3];
       SlabArgs sl;
       int rc;
-      FusedParams<T> prm;
+      FusedParams<T, P> prm;
     };
     constexpr int kEntries = 4;
     static Entry cache[kEntries];
@@ -1516,16 +1522,19 @@ static int fused_radius(const fdx_plan_t plans[3], const T* const in[3], T* cons
   using Tr = OpTraits<OP>;
   constexpr int V = 16 / sizeof(T);
   if (env_int("FDX_FUSED_DISABLE", 0)) return 0;
-  const int P = plans[0]->hi;
-  if (P < 1 || P > 6) return 0;
+  // The kernel radius is the largest reach of any axis' main stencil.  An axis with a shorter or one-sided stencil
+  // (per-axis accuracy, method = "forward" / "backward": offsets 0..L or -L..0, finite_diff.py:118-165) runs as a
+  // radius-P stencil whose missing taps are zero: the same sums, the taps outside the grid multiply TMA's zero fill.
+  int P = 0;
   for (int k = 0; k < 3; ++k) {
     const fdx_plan_s* p = plans[k];
-    if (p->lo != -P || p->hi != P) return 0;
-    if (k > 0 && (p->nl < P || p->nr < P)) return 0;   // in-plane axes never have halos
-    if (p->nl + p->nr > p->n) return 0;                 // dense (tiny-n) plans
+    if (p->lo > 0 || p->hi < 0) return 0;
+    P = std::max(P, std::max(-p->lo, p->hi));
+    if (p->nl < -p->lo || p->nr < p->hi) return 0;  // every main row must reach its (non-zero) taps inside the grid
+    if (p->nl + p->nr > p->n) return 0;              // dense (tiny-n) plans
     if (p->n < 1) return 0;
   }
-  if (plans[0]->nl < P || plans[0]->nr < P) return 0;
+  if (P < 1 || P > 6) return 0;
   if (plans[2]->n % V != 0) return 0;
   if ((int64_t)plans[1]->n * plans[2]->n * (int64_t)sizeof(T) > 0x7fffffffLL) return 0;  // 32-bit plane stride (bytes) in the kernel
   for (int f = 0; f < Tr::NIN; ++f)

@@ -61,8 +61,10 @@ def _match_fused(terms: Sequence[Term], n_in: int, n_out: int, spatial):
     """Recognise the four fused 3-D shapes.  Returns (kind, per-axis terms) or None."""
     if len(spatial) != 3 or not terms:
         return None
+    # every axis brings its own plan (derivative, accuracy and method may differ from axis to axis: the kernels run
+    # at the largest radius and pad shorter / one-sided stencils with zero taps); only the adjoint flag is shared
     t0 = terms[0]
-    if any((t.derivative, t.accuracy, t.method, t.transposed) != (t0.derivative, t0.accuracy, t0.method, t0.transposed) for t in terms):
+    if any(t.transposed != t0.transposed for t in terms):
         return None
     by = {(t.co, t.ci, t.axis): t for t in terms}
     if len(by) != len(terms):
@@ -83,7 +85,7 @@ def _match_fused(terms: Sequence[Term], n_in: int, n_out: int, spatial):
             for k in range(3):
                 tp = next(by[key] for key in plus if key[2] == k)
                 tm = next(by[key] for key in minus if key[2] == k)
-                if tp.alpha != -tm.alpha:
+                if tp.alpha != -tm.alpha or (tp.derivative, tp.accuracy, tp.method) != (tm.derivative, tm.accuracy, tm.method):
                     return None
                 axis_terms.append(tp)
             return "curl", axis_terms

@@ -115,6 +115,30 @@ def _okw(op, kw):
     return dict(kw, keepdims=False) if op == "divergence" else kw
 
 
+# ------------------------------------------------ operator-level vjp against the oracle (small grids, every accuracy)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_operator_level_vjp_equals_the_oracles_transposed_matrices(dtype):
+    """vjp of every fused 3-D operator = sum of D_k^T g over its terms with D_k the oracle's dense matrix (what jax.grad
+    through the reference computes), on the whole grid, for every radius the fused kernels cover and all three methods."""
+    shape = (30, 34, 40)
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    whole = [tuple(slice(0, n) for n in shape)]
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    for method, accs in (("central", (1, 2, 4, 6, 8, 10)), ("forward", (1, 3, 5)), ("backward", (2, 4))):
+        for acc in accs:
+            for op in ("laplacian", "gradient", "divergence", "curl"):
+                d = 2 if op == "laplacian" else 1
+                if method != "central" and d + acc - 1 > 6:
+                    continue
+                kw = dict(accuracy=acc, step_size=(0.1, 0.2, 0.3), method=method)
+                x = torch.randn(shape if N_IN[op] == 1 else (3,) + shape, device="cuda", dtype=dtype, generator=gen).requires_grad_(True)
+                out = _call(op, x, kw)
+                g = torch.randn(out.shape, device="cuda", dtype=dtype, generator=gen)
+                (gx,) = torch.autograd.grad(out, x, g)
+                assert _cabi.last_kernel().startswith("fused_"), (op, kw, _cabi.last_kernel())
+                check_vjp_bricks(op, g, gx, kw, tol, bricks=whole)
+
+
 # ------------------------------------------------------------------------- config 3: 512^3 fp32
 @pytest.mark.parametrize("op", ["laplacian", "gradient", "divergence", "curl"])
 def test_config3_512cubed_fp32_forward_and_vjp(op):

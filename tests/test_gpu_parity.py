@@ -252,10 +252,8 @@ def test_fused_kernels_cover_forward_and_adjoint():
 
     x = torch.randn(48, 40, 64, device="cuda", requires_grad=True)
     f = torch.randn(3, 48, 40, 64, device="cuda", requires_grad=True)
-    for acc in (2, 4, 6, 8):
+    for acc in (2, 4, 6, 8, 10):
         for name, arg, kw in (("laplacian", x, {}), ("gradient", x, {}), ("divergence", f, {"keepdims": False}), ("curl", f, {})):
-            if acc == 8 and name == "laplacian":
-                pass
             out = getattr(fdx, name)(arg, accuracy=acc, step_size=0.1, **kw)
             assert _cabi.last_kernel().startswith("fused_"), (name, acc, _cabi.last_kernel())
             g = torch.randn_like(out)
@@ -267,8 +265,45 @@ def test_fused_kernels_cover_forward_and_adjoint():
             tol = 2e-5
             assert ((out - out2).abs().max() / out2.abs().max()).item() < tol, (name, acc)
             assert ((gx - gx2).abs().max() / gx2.abs().max()).item() < tol, (name, acc)
-            if acc <= 4:
-                assert fused_bwd.startswith("fused_"), (name, acc, fused_bwd)
+            # the transposed plans (bands of P + L rows) stay on the fused kernels at every accuracy (round 2: the band
+            # tables of the parameter block are sized by the radius)
+            assert fused_bwd.startswith("fused_"), (name, acc, fused_bwd)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_path_covers_one_sided_methods_and_per_axis_accuracy(dtype):
+    """method = "forward" / "backward" (finite_diff.py:118-165) and accuracy tuples (:335-336, :562-563) run on the
+    fused single-pass kernels as radius-max stencils with zero taps, forward and vjp, and meet the oracle."""
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal((40, 44, 72)).astype(dtype)
+    f = rng.standard_normal((3, 36, 40, 64)).astype(dtype)
+    cases = []
+    for method in ("forward", "backward"):
+        cases += [("laplacian", x, dict(accuracy=2, step_size=0.5, method=method)),       # d + a - 1 = 3
+                  ("laplacian", x, dict(accuracy=4, step_size=(0.1, 0.2, 0.3), method=method)),  # 5
+                  ("gradient", x, dict(accuracy=4, step_size=0.1, method=method)),      # 4
+                  ("divergence", f, dict(accuracy=6, step_size=0.1, method=method, keepdims=False)),  # 6
+                  ("curl", f, dict(accuracy=3, step_size=0.1, method=method))]
+    cases += [("laplacian", x, dict(accuracy=(2, 4, 6), step_size=(0.1, 0.2, 0.3))),
+              ("laplacian", x, dict(accuracy=(8, 2, 4), step_size=0.2)),
+              ("gradient", x, dict(accuracy=(6, 1, 3), step_size=0.2)),
+              ("divergence", f, dict(accuracy=(1, 8, 2), step_size=0.2)),
+              ("curl", f, dict(accuracy=(2, 6, 4), step_size=(0.1, 0.2, 0.3)))]
+    for op, arr, kw in cases:
+        xt = _gpu(arr).requires_grad_(True)
+        out = getattr(fdx, op)(xt, **kw)
+        assert _cabi.last_kernel().startswith("fused_"), (op, kw, _cabi.last_kernel())
+        ref = getattr(O, op)(arr, **kw)
+        err = parity_error(op, arr, kw, out.detach().cpu().numpy(), ref)
+        assert err <= TOL[np.dtype(dtype)], (op, kw, err)
+        g = torch.randn_like(out)
+        (gx,) = torch.autograd.grad(out, xt, g)
+        assert _cabi.last_kernel().startswith("fused_"), (op, kw, "vjp", _cabi.last_kernel())
+        with _env(FDX_FUSED_DISABLE=1):
+            xt2 = _gpu(arr).requires_grad_(True)
+            (gx2,) = torch.autograd.grad(getattr(fdx, op)(xt2, **kw), xt2, g)
+        tol = 3e-5 if dtype == np.float32 else 1e-11
+        assert ((gx - gx2).abs().max() / gx2.abs().max()).item() < tol, (op, kw)
 
 
 def test_double_backward_is_the_operator_again():
