@@ -253,8 +253,8 @@ static int dispatch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t oute
 #define FDX_CASE(W_) \
   case W_:           \
     return launch_stream<T, V, W_, ACC>(p, x, out, outer, inner, alpha, st, band_done);
-    FDX_CASE(2) FDX_CASE(3) FDX_CASE(4) FDX_CASE(5) FDX_CASE(6) FDX_CASE(7) FDX_CASE(8) FDX_CASE(9) FDX_CASE(10)
-    FDX_CASE(11) FDX_CASE(12) FDX_CASE(13)
+    FDX_CASE(1) FDX_CASE(2) FDX_CASE(3) FDX_CASE(4) FDX_CASE(5) FDX_CASE(6) FDX_CASE(7) FDX_CASE(8) FDX_CASE(9) FDX_CASE(10)
+    FDX_CASE(11) FDX_CASE(12) FDX_CASE(13) FDX_CASE(14) FDX_CASE(15) FDX_CASE(16)  // up to FDX_MAX_TAPS
 #undef FDX_CASE
     default:
       return FDX_EUNSUPPORTED;

@@ -31,6 +31,7 @@
 #include <cstring>
 #include <mutex>
 #include <type_traits>
+#include <vector>
 
 #pragma once
 #include "fdx_common.cuh"
@@ -625,10 +626,12 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
         if (c + q >= c1) cf[q] = 0;
         x[q] = load(cc);
       }
+      // a tap whose coefficient is exactly zero (the padding of the last batch, zeros inside a transposed band) is
+      // skipped, as the axis kernels' band_element does: 0 * inf must not turn a band row into NaN
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int v = 0; v < V; ++v) a.v[v] = fma(cf[q], x[q].v[v], a.v[v]);
+        for (int v = 0; v < V; ++v) a.v[v] = cf[q] != (T)0 ? fma(cf[q], x[q].v[v], a.v[v]) : a.v[v];
     }
     return a;
   };
@@ -1170,11 +1173,61 @@ static SlabArgs slab_args(const fdx_plan_t plans[3], const fdx_slab* s) {
   return SlabArgs{s->z_begin, s->z_end, s->in_first, s->in_planes, s->out_first, s->z_begin2, s->z_end2 > s->z_begin2 ? s->z_end2 : s->z_begin2};
 }
 
+// A plan as the radius-P kernel wants it: at least P band rows on either side.  The kernel assumes that every MAIN row
+// finds all of its 2P + 1 taps inside the grid (zero taps included: the z queue completes an output plane P planes
+// later, the in-plane halos are P wide).  A one-sided or shorter stencil has fewer band rows than P (method="backward":
+// none on the right); the rows in between become band rows that carry the main stencil as dense taps -- the same sums.
+struct PaddedPlan {
+  fdx_plan_s p;  // h_band_l / h_band_r point into the vectors below; band_l / band_r (device) are unused here
+  std::vector<double> bl, br;
+};
+static bool pad_plan(PaddedPlan& out, const fdx_plan_s* src, int P) {
+  out.p = *src;
+  const int n = src->n, lo = src->lo, hi = src->hi, taps = hi - lo + 1;
+  const int nl = std::max(src->nl, std::min(P, n)), nr = std::max(src->nr, std::min(P, n));
+  const int wl = std::max(src->wl, nl + hi), wr = std::max(src->wr, nr - lo);
+  if (nl + nr > n || wl > n || wr > n) return false;
+  out.bl.assign((size_t)nl * wl, 0.0), out.br.assign((size_t)nr * wr, 0.0);
+  for (int r = 0; r < nl; ++r)
+    for (int c = 0; c < wl; ++c) {
+      double v = 0.0;
+      if (r < src->nl)
+        v = c < src->wl ? src->h_band_l[r * src->wl + c] : 0.0;
+      else if (c - r >= lo && c - r <= hi)
+        v = src->main_taps[c - r - lo];
+      out.bl[(size_t)r * wl + c] = v;
+    }
+  for (int r = 0; r < nr; ++r) {  // row n - nr + r, columns n - wr + c
+    const int sr = r - (nr - src->nr);  // row of the source's right band (negative: a main row)
+    for (int c = 0; c < wr; ++c) {
+      double v = 0.0;
+      if (sr >= 0) {
+        const int sc = c - (wr - src->wr);
+        v = sc >= 0 ? src->h_band_r[sr * src->wr + sc] : 0.0;
+      } else {
+        const int o = (wr - nr) + r;  // column of the row's own element
+        if (c - o >= lo && c - o <= hi) v = src->main_taps[c - o - lo];
+      }
+      out.br[(size_t)r * wr + c] = v;
+    }
+  }
+  (void)taps;
+  out.p.nl = nl, out.p.wl = wl, out.p.nr = nr, out.p.wr = wr;
+  out.p.h_band_l = out.bl.data(), out.p.h_band_r = out.br.data();
+  return true;
+}
+
 // Everything of a launch that does not depend on the data pointers: band tables, x-band layouts, tile counts, the
 // list of z chunks.  Cached per (plans, alpha, slab) by launch_cfg.  prm.n_chunks == 0 on return: nothing to do.
 template <Op OP, typename T, int P, typename CFG>
-static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans[3], const double alpha[3], const SlabArgs& sl) {
+static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans_in[3], const double alpha[3], const SlabArgs& sl) {
   using G = Geometry<OP, T, P, CFG>;
+  PaddedPlan padded[3];
+  const fdx_plan_s* plans[3];
+  for (int k = 0; k < 3; ++k) {
+    if (!pad_plan(padded[k], plans_in[k], P)) return FDX_EUNSUPPORTED;
+    plans[k] = &padded[k].p;
+  }
   const int n0 = plans[0]->n, n1 = plans[1]->n, n2 = plans[2]->n;
   (void)n1;
   prm.n_chunks = 0;
@@ -1548,10 +1601,12 @@ static int fused_radius(const fdx_plan_t plans[3], const T* const in[3], T* cons
     const int zb = r ? sl.z_begin2 : sl.z_begin, ze = r ? sl.z_end2 : sl.z_end;
     if (ze <= zb) continue;
     const fdx_plan_s* p0 = plans[0];
+    const int nl = std::max(p0->nl, P), nr = std::max(p0->nr, P);  // (the kernel's band rows: see pad_plan)
+    const int wl = std::max(p0->wl, nl + p0->hi), wr = std::max(p0->wr, nr - p0->lo);
     int lo = zb - P < 0 ? 0 : zb - P;
     int hi = ze + P > p0->n ? p0->n : ze + P;
-    if (zb < p0->nl) lo = 0, hi = hi > p0->wl ? hi : p0->wl;
-    if (ze > p0->n - p0->nr) lo = lo < p0->n - p0->wr ? lo : p0->n - p0->wr, hi = p0->n;
+    if (zb < nl) lo = 0, hi = hi > wl ? hi : wl;
+    if (ze > p0->n - nr) lo = lo < p0->n - wr ? lo : p0->n - wr, hi = p0->n;
     if (lo < sl.in_first || hi > sl.in_first + sl.in_planes) return -1;
     if (zb < sl.out_first) return -1;
   }

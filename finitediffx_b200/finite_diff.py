@@ -96,10 +96,40 @@ _fused_memo: dict = {}
 _plan_mod._dependent_caches.append(_fused_memo.clear)
 
 
+def _match_groups(terms: Sequence[Term], n_in: int, n_out: int, spatial):
+    """A term list as fused launches: [(kind, axis terms, first input field, first output field)] or None.
+    Either the whole list is one fused operator, or it splits into independent gradients of single input fields with
+    consecutive output fields -- the jacobian (finite_diff.py:392-401: one gradient per component, C x D axis passes
+    in the reference) becomes C single-pass launches -- or, transposed, into divergences (the jacobian's vjp)."""
+    m = _match_fused(terms, n_in, n_out, spatial)
+    if m is not None:
+        return [(m[0], m[1], 0, 0)]
+    if len(spatial) != 3 or not terms or len(terms) % 3:
+        return None
+    groups = []
+    for by_in in (True, False):  # gradients grouped by input field / divergences grouped by output field
+        buckets: dict = {}
+        for t in terms:
+            buckets.setdefault(t.ci if by_in else t.co, []).append(t)
+        groups = []
+        for key, ts in sorted(buckets.items()):
+            base = min((t.co if by_in else t.ci) for t in ts)
+            local = [dc.replace(t, co=t.co - base, ci=0) if by_in else dc.replace(t, ci=t.ci - base, co=0) for t in ts]
+            m = _match_fused(tuple(local), 1 if by_in else 3, 3 if by_in else 1, spatial)
+            if m is None or m[0] != ("gradient" if by_in else "divergence"):
+                groups = None
+                break
+            groups.append((m[0], m[1], key if by_in else base, base if by_in else key))
+        if groups:
+            return groups
+    return None
+
+
 def _fused_lookup(terms, n_in: int, n_out: int, spatial, dtype, device):
-    """Memoised recognition of a term list as a fused 3-D operator: a prepared ``_cabi.FusedLauncher`` or None.
-    The key uses the identity of the term tuple (``_memo_terms`` hands out the same tuple for repeated calls, and the
-    entry keeps it alive), so a hit costs one small-tuple hash instead of hashing every Term."""
+    """Memoised recognition of a term list as fused 3-D launches: a tuple of (prepared ``_cabi.FusedLauncher``, first
+    input field, first output field) or None.  The key uses the identity of the term tuple (``_memo_terms`` hands out
+    the same tuple for repeated calls, and the entry keeps it alive), so a hit costs one small-tuple hash instead of
+    hashing every Term."""
     key = (id(terms), n_in, n_out, spatial, dtype, device.index)
     hit = _fused_memo.get(key)
     if hit is not None and hit[0] is terms:
@@ -107,18 +137,19 @@ def _fused_lookup(terms, n_in: int, n_out: int, spatial, dtype, device):
     vkey = (terms, n_in, n_out, spatial, dtype, device.index)  # an equal term list built anew (tensor arguments)
     hit = _fused_memo.get(vkey)
     if hit is not None:
-        launcher = hit[1]
+        launches = hit[1]
     else:
-        m = _match_fused(terms, n_in, n_out, spatial)
-        launcher = None
-        if m is not None:
-            kind, axis_terms = m
-            launcher = _cabi.FusedLauncher(kind, tuple(t.plan(spatial[k]) for k, t in enumerate(axis_terms)), tuple(t.alpha for t in axis_terms), dtype, device)
+        groups = _match_groups(terms, n_in, n_out, spatial)
+        launches = None
+        if groups is not None:
+            launches = tuple(
+                (_cabi.FusedLauncher(kind, tuple(t.plan(spatial[k]) for k, t in enumerate(axis_terms)), tuple(t.alpha for t in axis_terms), dtype, device), fi, fo)
+                for kind, axis_terms, fi, fo in groups)
         if len(_fused_memo) > 512:
             _fused_memo.clear()
-        _fused_memo[vkey] = (terms, launcher)
-    _fused_memo[key] = (terms, launcher)
-    return launcher
+        _fused_memo[vkey] = (terms, launches)
+    _fused_memo[key] = (terms, launches)
+    return launches
 
 
 def _execute(terms: Sequence[Term], x: torch.Tensor, n_out: int) -> torch.Tensor:
@@ -127,14 +158,26 @@ def _execute(terms: Sequence[Term], x: torch.Tensor, n_out: int) -> torch.Tensor
     out = torch.empty((n_out,) + spatial, dtype=x.dtype, device=x.device)
     if x.numel() == 0:
         return out
-    launcher = _fused_lookup(terms, n_in, n_out, spatial, x.dtype, x.device) if len(spatial) == 3 else None
-    if launcher is not None:
+    launches = _fused_lookup(terms, n_in, n_out, spatial, x.dtype, x.device) if len(spatial) == 3 else None
+    if launches is not None:
         esz = x.element_size()
+        xs, os_ = x.stride(0) * esz, out.stride(0) * esz
+        xp, op = x.data_ptr(), out.data_ptr()
+        ok, covered = True, 0
         with _cabi._on_device(x.device):
-            rc = launcher.launch(x.data_ptr(), x.stride(0) * esz, out.data_ptr(), out.stride(0) * esz)
-        if rc == 0:
-            if n_out > 3 and launcher.kind == "gradient":
-                out[3:].zero_()
+            for launcher, fi, fo in launches:
+                if launcher.launch(xp + fi * xs, xs, op + fo * os_, os_) != 0:
+                    ok = False  # (the fused kernels do not cover this call: everything goes through the axis kernels)
+                    break
+                covered += launcher.nout
+        if ok:
+            if covered < n_out:  # fields no term writes (the vjp of a divergence that ignores extra components)
+                written = set()
+                for launcher, fi, fo in launches:
+                    written.update(range(fo, fo + launcher.nout))
+                for co in range(n_out):
+                    if co not in written:
+                        out[co].zero_()
             return out
     written = [False] * n_out
     for t in terms:
@@ -215,6 +258,7 @@ def _to_device(array):
 
 # ------------------------------------------------------------------ host arrays: streamed slabs
 _streamers: dict = {}
+_streamer_lock = __import__("threading").Lock()
 
 
 def _host_streamed(kind: str, array, accuracy, step_size, method: str, n_out: int):
@@ -251,8 +295,9 @@ def _host_streamed(kind: str, array, accuracy, step_size, method: str, n_out: in
     key = (kind, spatial, t.dtype, acc[0], tuple(float(h) for h in steps), dev.index, _slab.DEFAULT_SLAB_BYTES)
     st = _streamers.get(key)
     if st is None:
-        if len(_streamers) > 4:
-            _streamers.clear()
+        # a streamer keeps 3 rotating sets of input and output slabs in HBM (~0.4-0.8 GB): at most two stay cached
+        while len(_streamers) >= 2:
+            _streamers.pop(next(iter(_streamers)))
         st = _streamers[key] = _slab.HostStreamer(spec, t.dtype, dev, slab_planes=max(8, _slab.DEFAULT_SLAB_BYTES // max(1, spatial[1] * spatial[2] * t.element_size())))
     t = t.contiguous()
     if not t.is_pinned():
@@ -263,7 +308,8 @@ def _host_streamed(kind: str, array, accuracy, step_size, method: str, n_out: in
     xs = [t] if nin == 1 else [t[0], t[1], t[2]]
     outs = [out] if n_out == 1 else [out[k] for k in range(n_out)]
     try:
-        st.run(xs, outs)
+        with _streamer_lock:  # the streamer's buffers, streams and events are shared state: one call at a time
+            st.run(xs, outs)
     except _cabi.FdxError:
         return None
     torch.cuda.current_stream(dev).synchronize()
@@ -432,15 +478,57 @@ def hessian(array, *, accuracy=2, step_size=1, method: MethodKind = "central"):
     nd = x.ndim
     accuracy = _check_and_return(accuracy, nd, "accuracy")
     step_size = _check_and_return(step_size, nd, "step_size")
-    xf = x.unsqueeze(0)
-    table = {}
-    for k in range(nd):
-        table[2 * k] = _run(xf, [Term(0, 0, k, 2, int(accuracy[k]), method, _alpha(step_size[k], 2))], 1)
+    # F[key] as the reference's dict ends up (:497-521): the diagonal keys 2k first, then the mixed keys a1 + a2 in
+    # `combinations` order, later entries replacing earlier ones (for ndim >= 3, key 2 is d2/dx0dx2, not d2/dx1^2)
+    producer = {2 * k: (k,) for k in range(nd)}
     for a1, a2 in combinations(range(nd), 2):
-        inner = _run(xf, [Term(0, 0, a1, 1, int(accuracy[a1]), method, _alpha(step_size[a1], 1))], 1)
-        table[a1 + a2] = _run(inner, [Term(0, 0, a2, 1, int(accuracy[a2]), method, _alpha(step_size[a2], 1))], 1)
-    rows = [torch.cat([table[i + j] for j in range(nd)], dim=0) for i in range(nd)]
-    return restore(torch.stack(rows, dim=0))
+        producer[a1 + a2] = (a1, a2)
+
+    def d1(k):
+        return Term(0, 0, k, 1, int(accuracy[k]), method, _alpha(step_size[k], 1))
+
+    def d2(k):
+        return Term(0, 0, k, 2, int(accuracy[k]), method, _alpha(step_size[k], 2))
+
+    xf = x.unsqueeze(0)
+    if x.requires_grad and torch.is_grad_enabled():
+        # differentiable composition: one pass per first derivative that a mixed entry needs (the reference recomputes
+        # it per pair), one per surviving table entry, ONE stack
+        first, table = {}, {}
+        for key, who in producer.items():
+            if len(who) == 1:
+                table[key] = _run(xf, [d2(who[0])], 1)
+            else:
+                a1, a2 = who
+                if a1 not in first:
+                    first[a1] = _run(xf, [d1(a1)], 1)
+                table[key] = _run(first[a1], [d1(a2)], 1)
+        flat = torch.cat([table[i + j] for i in range(nd) for j in range(nd)], dim=0)
+        return restore(flat.reshape((nd, nd) + tuple(x.shape)))
+    # no gradient wanted: every surviving entry is computed ONCE, straight into its first slot of the (nd, nd, ...)
+    # result, and copied to the other slots with i + j == key (the reference: nd + nd (nd - 1) differences, each a
+    # concatenate, then nd + 1 stacks).  3-D: 7 axis passes + 4 slot copies instead of 9 passes and two full copies.
+    for t in [d2(k) for k in range(nd)] + [d1(k) for k in range(nd)]:
+        t.plan(x.shape[t.axis])  # the reference's ValueErrors, before anything is launched
+    out = torch.empty((nd, nd) + tuple(x.shape), dtype=x.dtype, device=x.device)
+    first = {}
+    for key, who in producer.items():
+        slots = [(i, key - i) for i in range(nd) if 0 <= key - i < nd]
+        dst = out[slots[0]]
+        if len(who) == 1:
+            t = d2(who[0])
+            _cabi.axis_apply(t.plan(x.shape[t.axis]), x, dst, t.axis, t.alpha)
+        else:
+            a1, a2 = who
+            if a1 not in first:
+                t = d1(a1)
+                first[a1] = torch.empty_like(x)
+                _cabi.axis_apply(t.plan(x.shape[a1]), x, first[a1], a1, t.alpha)
+            t = d1(a2)
+            _cabi.axis_apply(t.plan(x.shape[a2]), first[a1], dst, a2, t.alpha)
+        for sl in slots[1:]:
+            out[sl].copy_(dst)
+    return restore(out)
 
 
 def laplacian(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
