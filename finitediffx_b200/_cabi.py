@@ -77,6 +77,16 @@ EXPORTS = (
     "fdx_launch_count",
     "fdx_last_kernel",
     "fdx_reload_env",
+    "fdx_axis_apply_dev_alpha_f32",
+    "fdx_axis_apply_dev_alpha_f64",
+    "fdx_laplacian3d_dev_alpha_f32",
+    "fdx_laplacian3d_dev_alpha_f64",
+    "fdx_divergence3d_dev_alpha_f32",
+    "fdx_divergence3d_dev_alpha_f64",
+    "fdx_gradient3d_dev_alpha_f32",
+    "fdx_gradient3d_dev_alpha_f64",
+    "fdx_curl3d_dev_alpha_f32",
+    "fdx_curl3d_dev_alpha_f64",
 )
 
 
@@ -103,6 +113,11 @@ def load():
         lib.fdx_plan_destroy.argtypes = [vp]
         for sfx in ("f32", "f64"):
             getattr(lib, f"fdx_axis_apply_{sfx}").argtypes = [vp, vp, vp, i64, i64, dbl, i32, vp]
+            getattr(lib, f"fdx_axis_apply_dev_alpha_{sfx}").argtypes = [vp, vp, vp, i64, i64, vp, dbl, i32, vp]
+            getattr(lib, f"fdx_laplacian3d_dev_alpha_{sfx}").argtypes = [C.POINTER(vp), vp, vp, vp, vp]
+            getattr(lib, f"fdx_divergence3d_dev_alpha_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, vp, vp]
+            getattr(lib, f"fdx_gradient3d_dev_alpha_{sfx}").argtypes = [C.POINTER(vp), vp, C.POINTER(vp), vp, vp]
+            getattr(lib, f"fdx_curl3d_dev_alpha_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp]
             getattr(lib, f"fdx_laplacian3d_{sfx}").argtypes = [C.POINTER(vp), vp, vp, C.POINTER(dbl), C.POINTER(Slab), vp]
             getattr(lib, f"fdx_divergence3d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(dbl), C.POINTER(Slab), vp]
             getattr(lib, f"fdx_gradient3d_{sfx}").argtypes = [C.POINTER(vp), vp, C.POINTER(vp), C.POINTER(dbl), C.POINTER(Slab), vp]
@@ -236,6 +251,47 @@ def axis_apply(plan: AxisPlan, x: torch.Tensor, out: torch.Tensor, axis: int, al
             fn(dp.handle, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), outer, inner, float(alpha), int(bool(accumulate)), _stream_ptr(x.device)),
             "fdx_axis_apply",
         )
+
+
+def axis_apply_dev_alpha(plan: AxisPlan, x: torch.Tensor, out: torch.Tensor, axis: int, alpha_dev: torch.Tensor, sign: float = 1.0,
+                         accumulate: bool = False):
+    """out (+)= sign * alpha_dev * D_axis x with the scale read on the device (``alpha_dev``: a float64 CUDA tensor of one
+    element, e.g. an element view of a vector of scales).  No host read of the scale: no synchronisation, capture-safe."""
+    _require(x, "x")
+    _require(out, "out")
+    assert x.shape == out.shape and x.dtype == out.dtype
+    assert alpha_dev.is_cuda and alpha_dev.dtype == torch.float64 and alpha_dev.numel() >= 1
+    if x.numel() == 0:
+        return
+    shape = x.shape
+    assert shape[axis] == plan.n, (shape, axis, plan.n)
+    outer = int(np.prod(shape[:axis], dtype=np.int64)) if axis > 0 else 1
+    inner = int(np.prod(shape[axis + 1 :], dtype=np.int64)) if axis + 1 < len(shape) else 1
+    dp = device_plan(plan, x.device)
+    with _on_device(x.device):
+        fn = getattr(load(), f"fdx_axis_apply_dev_alpha_{_sfx(x)}")
+        check(
+            fn(dp.handle, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), outer, inner, C.c_void_p(alpha_dev.data_ptr()), float(sign),
+               int(bool(accumulate)), _stream_ptr(x.device)),
+            "fdx_axis_apply_dev_alpha",
+        )
+
+
+def fused3d_dev_alpha(kind: str, plans: Sequence[AxisPlan], xs, outs, alpha_dev: torch.Tensor) -> None:
+    """The 3-D operators with the three per-axis scales read on the device (``alpha_dev``: float64 CUDA tensor, 3 elements)."""
+    x_one, o_one = isinstance(xs, torch.Tensor), isinstance(outs, torch.Tensor)
+    first = xs if x_one else xs[0]
+    dev = first.device
+    assert alpha_dev.is_cuda and alpha_dev.dtype == torch.float64 and alpha_dev.numel() == 3 and alpha_dev.is_contiguous()
+    for t in ((xs,) if x_one else tuple(xs)) + ((outs,) if o_one else tuple(outs)):
+        _require(t, "tensor")
+    keep, hp = _handles(plans, dev)
+    fn = getattr(load(), f"fdx_{kind}3d_dev_alpha_{_sfx(first)}")
+    xin = C.c_void_p(xs.data_ptr()) if x_one else _ptrs(xs)
+    xout = C.c_void_p(outs.data_ptr()) if o_one else _ptrs(outs)
+    with _on_device(dev):
+        check(fn(hp, xin, xout, C.c_void_p(alpha_dev.data_ptr()), _stream_ptr(dev)), f"fdx_{kind}3d_dev_alpha")
+    del keep
 
 
 def _handles(plans: Sequence[AxisPlan], device):

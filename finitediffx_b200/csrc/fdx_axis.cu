@@ -30,11 +30,19 @@ struct FusedBand {
   T alpha;
   int64_t n, inner, outer;
   int blocks;  // leading CTAs that work on band elements (0: the caller launches axis_band_kernel)
+  // runtime scale read ON THE DEVICE (the *_dev_alpha entry points: alpha is a traced value in the caller's graph and
+  // must not be fetched by the host); nullptr: the scale is already folded into the taps / `alpha` on the host
+  const double* alpha_dev;
 };
+
+template <typename T>
+__device__ __forceinline__ T dev_scale(const double* alpha_dev) {
+  return alpha_dev ? (T)__ldg(alpha_dev) : (T)1;
+}
 
 template <typename T, bool ACC>
 __device__ __forceinline__ void band_element(const T* __restrict__ x, T* __restrict__ out, int64_t n, int64_t inner,
-                                             int64_t outer, const Bands& b, T alpha, int64_t g) {
+                                             int64_t outer, const Bands& b, T alpha, int64_t g, const double* alpha_dev = nullptr) {
   const int nb = b.nl + b.nr;
   if (g >= outer * nb * inner) return;
   const int64_t j = g % inner;
@@ -56,7 +64,7 @@ __device__ __forceinline__ void band_element(const T* __restrict__ x, T* __restr
     const T cf = (T)__ldg(coef + c);
     if (cf != (T)0) acc = fma(cf, __ldg(xp + (int64_t)c * inner), acc);
   }
-  acc *= alpha;
+  acc *= alpha * dev_scale<T>(alpha_dev);
   T* o_ptr = out + (o * n + row) * inner + j;
   *o_ptr = ACC ? *o_ptr + acc : acc;
 }
@@ -68,7 +76,7 @@ __global__ void __launch_bounds__(128) axis_stream_kernel(const T* __restrict__ 
                                                           int n_chunks, int64_t n_tiles, const __grid_constant__ Taps<T> taps,
                                                           const __grid_constant__ FusedBand<T> fb) {
   if ((int)blockIdx.x < fb.blocks) {
-    band_element<T, ACC>(x, out, fb.n, fb.inner, fb.outer, fb.b, fb.alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    band_element<T, ACC>(x, out, fb.n, fb.inner, fb.outer, fb.b, fb.alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, fb.alpha_dev);
     return;
   }
   int64_t b = (int64_t)blockIdx.x - fb.blocks;
@@ -85,6 +93,7 @@ __global__ void __launch_bounds__(128) axis_stream_kernel(const T* __restrict__ 
   T* op = out + (o * n + (int64_t)i0) * stride + jv * V;
 
   using VT = Vec<T, V>;
+  const T scale = dev_scale<T>(fb.alpha_dev);
   VT q[W];
 #pragma unroll
   for (int k = 0; k < W - 1; ++k) {
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(128) axis_stream_kernel(const T* __restrict__ 
       T acc = taps.c[0] * q[s % W].v[v];
 #pragma unroll
       for (int k = 1; k < W; ++k) acc = fma(taps.c[k], q[(s + k) % W].v[v], acc);
-      r.v[v] = acc;
+      r.v[v] = fb.alpha_dev ? acc * scale : acc;
     }
     if constexpr (ACC) {
       VT old = ld_cached<T, V>(op);
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(256) axis_row_kernel(const T* __restrict__ x, 
                                                        int n_v, int r0, int r1, const __grid_constant__ Taps<T> taps,
                                                        const __grid_constant__ FusedBand<T> fb) {
   if ((int)blockIdx.x < fb.blocks) {
-    band_element<T, ACC>(x, out, fb.n, fb.inner, fb.outer, fb.b, fb.alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    band_element<T, ACC>(x, out, fb.n, fb.inner, fb.outer, fb.b, fb.alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, fb.alpha_dev);
     return;
   }
   const int64_t g = ((int64_t)blockIdx.x - fb.blocks) * blockDim.x + threadIdx.x;
@@ -159,12 +168,13 @@ __global__ void __launch_bounds__(256) axis_row_kernel(const T* __restrict__ x, 
     for (int v = 0; v < V; ++v) w[u * V + v] = r.v[v];
   }
   Vec<T, V> res;
+  const T scale = dev_scale<T>(fb.alpha_dev);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     T acc = taps.c[0] * w[v + LO - A * V];
 #pragma unroll
     for (int k = 1; k < W; ++k) acc = fma(taps.c[k], w[v + LO + k - A * V], acc);
-    res.v[v] = acc;
+    res.v[v] = fb.alpha_dev ? acc * scale : acc;
   }
   T* orow = out + row * ((int64_t)n_v * V) + i_first;
   if (i_first >= r0 && i_first + V <= r1) {
@@ -186,7 +196,8 @@ __global__ void __launch_bounds__(256) axis_row_kernel(const T* __restrict__ x, 
 // contiguous axis, any length/alignment: one thread per main-row output, taps through L1
 template <typename T, bool ACC>
 __global__ void __launch_bounds__(256) axis_row_scalar_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t outer,
-                                                              int n, int lo, int taps_n, int r0, int r1, const __grid_constant__ Taps<T> taps) {
+                                                              int n, int lo, int taps_n, int r0, int r1, const __grid_constant__ Taps<T> taps,
+                                                              const double* alpha_dev) {
   const int m = r1 - r0;
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= outer * m) return;
@@ -195,6 +206,7 @@ __global__ void __launch_bounds__(256) axis_row_scalar_kernel(const T* __restric
   const T* xr = x + row * n + i + lo;
   T acc = taps.c[0] * __ldg(xr);
   for (int k = 1; k < taps_n; ++k) acc = fma(taps.c[k], __ldg(xr + k), acc);
+  acc *= dev_scale<T>(alpha_dev);
   T* o = out + row * n + i;
   *o = ACC ? *o + acc : acc;
 }
@@ -202,16 +214,16 @@ __global__ void __launch_bounds__(256) axis_row_scalar_kernel(const T* __restric
 // ---------------------------------------------------------------------------------- axis_band
 template <typename T, bool ACC>
 __global__ void __launch_bounds__(256) axis_band_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n,
-                                                        int64_t inner, int64_t outer, Bands b, T alpha) {
-  band_element<T, ACC>(x, out, n, inner, outer, b, alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+                                                        int64_t inner, int64_t outer, Bands b, T alpha, const double* alpha_dev) {
+  band_element<T, ACC>(x, out, n, inner, outer, b, alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, alpha_dev);
 }
 
 // The band rows as leading CTAs of a main kernel with `threads` threads per CTA (blocks = 0 if there are none or
 // too many; the caller then launches axis_band_kernel).
 template <typename T>
-static FusedBand<T> fused_band(const fdx_plan_s* p, int64_t outer, int64_t inner, double alpha, int threads) {
+static FusedBand<T> fused_band(const fdx_plan_s* p, int64_t outer, int64_t inner, double alpha, int threads, const double* alpha_dev) {
   FusedBand<T> fb;
-  fb.b = bands_of(p), fb.alpha = (T)alpha, fb.n = p->n, fb.inner = inner, fb.outer = outer, fb.blocks = 0;
+  fb.b = bands_of(p), fb.alpha = (T)alpha, fb.n = p->n, fb.inner = inner, fb.outer = outer, fb.blocks = 0, fb.alpha_dev = alpha_dev;
   const int64_t total = outer * (int64_t)(p->nl + p->nr) * inner;
   const int64_t blocks = (total + threads - 1) / threads;
   if (blocks > 0 && blocks <= (1 << 20)) fb.blocks = (int)blocks;
@@ -221,7 +233,7 @@ static FusedBand<T> fused_band(const fdx_plan_s* p, int64_t outer, int64_t inner
 // ----------------------------------------------------------------------------------- dispatch
 template <typename T, int V, int W, bool ACC>
 static int launch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha,
-                         cudaStream_t st, bool* band_done) {
+                         cudaStream_t st, bool* band_done, const double* alpha_dev) {
   const int r0 = p->nl, r1 = p->n - p->nr;
   const int m = r1 - r0;
   if (m <= 0) return FDX_OK;
@@ -236,7 +248,7 @@ static int launch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer,
   rows = ((rows + W - 1) / W) * W;
   if (rows > m) rows = m;
   const int n_chunks = (m + rows - 1) / rows;
-  const FusedBand<T> fb = fused_band<T>(p, outer, inner, alpha, 128);
+  const FusedBand<T> fb = fused_band<T>(p, outer, inner, alpha, 128, alpha_dev);
   const int64_t blocks = n_tiles * n_chunks * outer + fb.blocks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   axis_stream_kernel<T, V, W, ACC><<<(unsigned)blocks, 128, 0, st>>>(x, out, p->n, inner_v, p->lo, r0, r1, rows, n_chunks,
@@ -248,11 +260,11 @@ static int launch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer,
 
 template <typename T, int V, bool ACC>
 static int dispatch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha,
-                           cudaStream_t st, bool* band_done) {
+                           cudaStream_t st, bool* band_done, const double* alpha_dev) {
   switch (p->hi - p->lo + 1) {
 #define FDX_CASE(W_) \
   case W_:           \
-    return launch_stream<T, V, W_, ACC>(p, x, out, outer, inner, alpha, st, band_done);
+    return launch_stream<T, V, W_, ACC>(p, x, out, outer, inner, alpha, st, band_done, alpha_dev);
     FDX_CASE(1) FDX_CASE(2) FDX_CASE(3) FDX_CASE(4) FDX_CASE(5) FDX_CASE(6) FDX_CASE(7) FDX_CASE(8) FDX_CASE(9) FDX_CASE(10)
     FDX_CASE(11) FDX_CASE(12) FDX_CASE(13) FDX_CASE(14) FDX_CASE(15) FDX_CASE(16)  // up to FDX_MAX_TAPS
 #undef FDX_CASE
@@ -262,10 +274,11 @@ static int dispatch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t oute
 }
 
 template <typename T, int V, int LO, int HI, bool ACC>
-static int launch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done) {
+static int launch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done,
+                      const double* alpha_dev) {
   const int n_v = p->n / V;
   const int64_t total = outer * n_v;
-  const FusedBand<T> fb = fused_band<T>(p, outer, 1, alpha, 256);
+  const FusedBand<T> fb = fused_band<T>(p, outer, 1, alpha, 256, alpha_dev);
   const int64_t blocks = (total + 255) / 256 + fb.blocks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   axis_row_kernel<T, V, LO, HI, ACC><<<(unsigned)blocks, 256, 0, st>>>(x, out, total, n_v, p->nl, p->n - p->nr,
@@ -276,13 +289,14 @@ static int launch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, do
 }
 
 template <typename T, int V, bool ACC>
-static int dispatch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done) {
+static int dispatch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done,
+                        const double* alpha_dev) {
   const int lo = p->lo, hi = p->hi;
 #define FDX_C(P_) \
-  if (lo == -P_ && hi == P_) return launch_row<T, V, -P_, P_, ACC>(p, x, out, outer, alpha, st, band_done);
+  if (lo == -P_ && hi == P_) return launch_row<T, V, -P_, P_, ACC>(p, x, out, outer, alpha, st, band_done, alpha_dev);
 #define FDX_F(L_)                                                                              \
-  if (lo == 0 && hi == L_) return launch_row<T, V, 0, L_, ACC>(p, x, out, outer, alpha, st, band_done); \
-  if (lo == -L_ && hi == 0) return launch_row<T, V, -L_, 0, ACC>(p, x, out, outer, alpha, st, band_done);
+  if (lo == 0 && hi == L_) return launch_row<T, V, 0, L_, ACC>(p, x, out, outer, alpha, st, band_done, alpha_dev); \
+  if (lo == -L_ && hi == 0) return launch_row<T, V, -L_, 0, ACC>(p, x, out, outer, alpha, st, band_done, alpha_dev);
   FDX_C(1) FDX_C(2) FDX_C(3) FDX_C(4) FDX_C(5) FDX_C(6)
   FDX_F(1) FDX_F(2) FDX_F(3) FDX_F(4) FDX_F(5) FDX_F(6) FDX_F(7) FDX_F(8) FDX_F(9) FDX_F(10) FDX_F(11)
 #undef FDX_C
@@ -292,7 +306,7 @@ static int dispatch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, 
 
 template <typename T, bool ACC>
 static int apply_impl(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha,
-                      cudaStream_t st) {
+                      cudaStream_t st, const double* alpha_dev) {
   constexpr int V = 16 / sizeof(T);
   const int m = p->n - p->nl - p->nr;
   const bool aligned16 = (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
@@ -301,18 +315,18 @@ static int apply_impl(const fdx_plan_s* p, const T* x, T* out, int64_t outer, in
   if (m > 0) {
     if (inner > 1) {
       if (aligned16 && inner % V == 0)
-        rc = dispatch_stream<T, V, ACC>(p, x, out, outer, inner, alpha, st, &band_done);
+        rc = dispatch_stream<T, V, ACC>(p, x, out, outer, inner, alpha, st, &band_done, alpha_dev);
       else
-        rc = dispatch_stream<T, 1, ACC>(p, x, out, outer, inner, alpha, st, &band_done);
+        rc = dispatch_stream<T, 1, ACC>(p, x, out, outer, inner, alpha, st, &band_done, alpha_dev);
     } else {
       rc = FDX_EUNSUPPORTED;
-      if (aligned16 && p->n % V == 0) rc = dispatch_row<T, V, ACC>(p, x, out, outer, alpha, st, &band_done);
+      if (aligned16 && p->n % V == 0) rc = dispatch_row<T, V, ACC>(p, x, out, outer, alpha, st, &band_done, alpha_dev);
       if (rc == FDX_EUNSUPPORTED) {
         const int64_t total = outer * m;
         const int64_t blocks = (total + 255) / 256;
         if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
         axis_row_scalar_kernel<T, ACC><<<(unsigned)blocks, 256, 0, st>>>(x, out, outer, p->n, p->lo, p->hi - p->lo + 1, p->nl,
-                                                                         p->n - p->nr, scaled_taps<T>(p, alpha));
+                                                                         p->n - p->nr, scaled_taps<T>(p, alpha), alpha_dev);
         count_launch("axis_row_scalar");
         rc = FDX_OK;
       }
@@ -325,7 +339,7 @@ static int apply_impl(const fdx_plan_s* p, const T* x, T* out, int64_t outer, in
     const int64_t total = outer * nb * inner;
     const int64_t blocks = (total + 255) / 256;
     if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
-    axis_band_kernel<T, ACC><<<(unsigned)blocks, 256, 0, st>>>(x, out, p->n, inner, outer, bands_of(p), (T)alpha);
+    axis_band_kernel<T, ACC><<<(unsigned)blocks, 256, 0, st>>>(x, out, p->n, inner, outer, bands_of(p), (T)alpha, alpha_dev);
     count_launch("axis_band");
     FDX_LAUNCH_CHECK();
   }
@@ -334,13 +348,13 @@ static int apply_impl(const fdx_plan_s* p, const T* x, T* out, int64_t outer, in
 
 template <typename T>
 static int apply_checked(fdx_plan_t plan, const T* x, T* out, int64_t outer, int64_t inner, double alpha, int accumulate,
-                         void* stream) {
+                         void* stream, const double* alpha_dev = nullptr) {
   if (!plan || !x || !out || outer < 0 || inner < 0) return FDX_EINVAL;
   if ((((uintptr_t)x | (uintptr_t)out) & (sizeof(T) - 1)) != 0) return FDX_EALIGN;
   if (outer == 0 || inner == 0 || plan->n == 0) return FDX_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  return accumulate ? apply_impl<T, true>(plan, x, out, outer, inner, alpha, st)
-                    : apply_impl<T, false>(plan, x, out, outer, inner, alpha, st);
+  return accumulate ? apply_impl<T, true>(plan, x, out, outer, inner, alpha, st, alpha_dev)
+                    : apply_impl<T, false>(plan, x, out, outer, inner, alpha, st, alpha_dev);
 }
 
 }  // namespace fdx
@@ -353,4 +367,18 @@ extern "C" int fdx_axis_apply_f32(fdx_plan_t plan, const float* x, float* out, i
 extern "C" int fdx_axis_apply_f64(fdx_plan_t plan, const double* x, double* out, int64_t outer, int64_t inner,
                                   double alpha, int accumulate, void* stream) {
   return fdx::apply_checked<double>(plan, x, out, outer, inner, alpha, accumulate, stream);
+}
+
+// ---- alpha read on the device (XLA custom calls: `step_size` is a traced value, finite_diff.py:168): the host never
+// touches it, so the call needs no synchronisation and is safe under stream capture.  out = sign * (*alpha_dev) * D x.
+extern "C" int fdx_axis_apply_dev_alpha_f32(fdx_plan_t plan, const float* x, float* out, int64_t outer, int64_t inner,
+                                            const double* alpha_dev, double sign, int accumulate, void* stream) {
+  if (!alpha_dev) return FDX_EINVAL;
+  return fdx::apply_checked<float>(plan, x, out, outer, inner, sign, accumulate, stream, alpha_dev);
+}
+
+extern "C" int fdx_axis_apply_dev_alpha_f64(fdx_plan_t plan, const double* x, double* out, int64_t outer, int64_t inner,
+                                            const double* alpha_dev, double sign, int accumulate, void* stream) {
+  if (!alpha_dev) return FDX_EINVAL;
+  return fdx::apply_checked<double>(plan, x, out, outer, inner, sign, accumulate, stream, alpha_dev);
 }

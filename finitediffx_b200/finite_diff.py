@@ -322,6 +322,91 @@ def _alpha(step, derivative: int) -> float:
     return 1.0 / (float(step) ** derivative)
 
 
+# ------------------------------------------------------------------ traced step_size (a device value)
+def _traced_steps(step_size, nd: int, device):
+    """``step_size`` as the reference sees it under ``jax.jit`` -- a traced DEVICE value (finite_diff.py:168: it is not a
+    static argument): a CUDA tensor, or a tensor that wants a gradient (or a tuple holding one).  Returns a float64
+    CUDA vector of ``nd`` step sizes that keeps the autograd graph, or None for concrete Python / NumPy values.  The
+    host never reads the values (no ``.item()``, no synchronisation: the call can be captured in a CUDA graph); the
+    kernels read the scales 1 / h**d on the device (the *_dev_alpha entry points)."""
+    def traced(v):
+        return isinstance(v, torch.Tensor) and (v.is_cuda or v.requires_grad)
+
+    if traced(step_size):
+        h = step_size.to(device=device, dtype=torch.float64).reshape(-1)
+        if h.numel() == 1:
+            return h.expand(nd)
+        return h.repeat_interleave(nd)[:nd]  # jnp.repeat(value, ndim), zipped against the axes (utils.py:29)
+    if isinstance(step_size, tuple) and any(traced(v) for v in step_size):
+        assert len(step_size) == nd, f"step_size must be a tuple of length {nd}"
+        return torch.stack([(v if isinstance(v, torch.Tensor) else torch.tensor(float(v))).to(device=device, dtype=torch.float64).reshape(()) for v in step_size])
+    return None
+
+
+def _execute_dev(terms: Sequence[Term], x: torch.Tensor, n_out: int, scale: torch.Tensor) -> torch.Tensor:
+    """``_execute`` with the per-axis scales read on the device: term.alpha carries the sign only."""
+    spatial = tuple(x.shape[1:])
+    out = torch.empty((n_out,) + spatial, dtype=x.dtype, device=x.device)
+    if x.numel() == 0:
+        return out
+    m = _match_fused(terms, x.shape[0], n_out, spatial) if len(spatial) == 3 else None
+    if m is not None and all(t.alpha == 1.0 for t in m[1]):
+        kind, axis_terms = m
+        plans = tuple(t.plan(spatial[k]) for k, t in enumerate(axis_terms))
+        xs = x[0] if kind in ("laplacian", "gradient") else [x[0], x[1], x[2]]
+        outs = out[0] if kind in ("laplacian", "divergence") else [out[0], out[1], out[2]]
+        _cabi.fused3d_dev_alpha(kind, plans, xs, outs, scale.contiguous())
+        for co in range(3 if kind in ("gradient", "curl") else 1, n_out):
+            out[co].zero_()
+        return out
+    written = [False] * n_out
+    for t in terms:
+        _cabi.axis_apply_dev_alpha(t.plan(spatial[t.axis]), x[t.ci], out[t.co], t.axis, scale[t.axis : t.axis + 1], sign=t.alpha, accumulate=written[t.co])
+        written[t.co] = True
+    for co, w in enumerate(written):
+        if not w:
+            out[co].zero_()
+    return out
+
+
+class _TracedStencilOp(torch.autograd.Function):
+    """A stencil operator whose step sizes are device values: out = sum_terms sign * h_axis**(-d) * D x.  Backward gives
+    the cotangent of the array (transposed terms, like ``_StencilOp``) AND of ``step_size`` -- jax.grad through the
+    reference yields both: d/dh [h**(-d) D x] = -d / h * (the term itself)."""
+
+    @staticmethod
+    def forward(ctx, x, h, terms, n_out):
+        d_axis = {t.axis: t.derivative for t in terms}
+        hd = h.detach()
+        scale = torch.stack([torch.pow(hd[k], -float(d_axis.get(k, 0))) for k in range(hd.numel())])  # 1 / h**d per axis, on the device
+        ctx.terms, ctx.n_in = terms, x.shape[0]
+        ctx.save_for_backward(x, h.detach(), scale)
+        return _execute_dev(terms, x, n_out, scale)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, h, scale = ctx.saved_tensors
+        g = g.contiguous()
+        gx = gh = None
+        if ctx.needs_input_grad[0]:
+            gx = _execute_dev(tuple(t.t() for t in ctx.terms), g, ctx.n_in, scale)
+        if ctx.needs_input_grad[1]:
+            gh = torch.zeros_like(h)
+            tmp = torch.empty_like(x[0])
+            for t in ctx.terms:  # one pass per term: <g, term> (only when the step sizes want a gradient)
+                _cabi.axis_apply_dev_alpha(t.plan(x.shape[1 + t.axis]), x[t.ci], tmp, t.axis, scale[t.axis : t.axis + 1], sign=t.alpha)
+                gh[t.axis] += (g[t.co].double() * tmp.double()).sum() * (-float(t.derivative)) / h[t.axis]
+        return gx, gh, None, None
+
+
+def _run_traced(x_fields: torch.Tensor, h: torch.Tensor, terms, n_out: int) -> torch.Tensor:
+    terms = tuple(terms)
+    for t in terms:
+        t.plan(x_fields.shape[1 + t.axis])
+    return _TracedStencilOp.apply(x_fields, h, terms, n_out)
+
+
 def _norm_axis(axis: int, ndim: int) -> int:
     if not -ndim <= axis < ndim:
         raise ValueError(f"axis {axis} is out of bounds for array of dimension {ndim}")
@@ -399,6 +484,11 @@ def difference(
     if x.ndim == 0:
         raise ValueError("difference needs an array with at least one axis")
     ax = _norm_axis(axis, x.ndim)
+    ht = _traced_steps(step_size, 1, x.device)
+    if ht is not None:  # a device value: the kernels read the scale themselves (no host read, no synchronisation)
+        one = torch.ones(1, dtype=torch.float64, device=x.device)
+        hv = torch.cat([one.expand(ax), ht[0:1], one.expand(x.ndim - ax - 1)])  # (device ops only: capturable)
+        return restore(_run_traced(x.unsqueeze(0), hv, [Term(0, 0, ax, int(derivative), int(accuracy), method, 1.0)], 1).squeeze(0))
     term = Term(0, 0, ax, int(derivative), int(accuracy), method, _alpha(step_size, derivative))
     return restore(_run(x.unsqueeze(0), [term], 1).squeeze(0))  # (a view both ways: select would cost a zero-fill in backward)
 
@@ -413,6 +503,10 @@ def gradient(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
     if streamed is not None:
         return streamed
     x, restore = _to_device(array)
+    ht = _traced_steps(step_size, x.ndim, x.device)
+    if ht is not None:
+        acc = _check_and_return(accuracy, x.ndim, "accuracy")
+        return restore(_run_traced(x.unsqueeze(0), ht, [Term(k, 0, k, 1, int(a), method, 1.0) for k, a in enumerate(acc)], x.ndim))
 
     def build():
         acc = _check_and_return(accuracy, x.ndim, "accuracy")
@@ -430,8 +524,12 @@ def jacobian(array, *, accuracy=1, step_size=1, method: MethodKind = "central"):
     x, restore = _to_device(array)
     nd = x.ndim - 1
     accuracy = _check_and_return(accuracy, nd, "accuracy")
-    step_size = _check_and_return(step_size, nd, "step_size")
     ncomp = x.shape[0]
+    ht = _traced_steps(step_size, nd, x.device)
+    if ht is not None:
+        terms = [Term(c * nd + k, c, k, 1, int(a), method, 1.0) for c in range(ncomp) for k, a in enumerate(accuracy)]
+        return restore(_run_traced(x, ht, terms, ncomp * nd).reshape((ncomp, nd) + tuple(x.shape[1:])))
+    step_size = _check_and_return(step_size, nd, "step_size")
     terms = [
         Term(c * nd + k, c, k, 1, int(a), method, _alpha(h, 1))
         for c in range(ncomp)
@@ -452,6 +550,13 @@ def divergence(array, *, accuracy=1, step_size=1, keepdims: bool = True, method:
         return streamed[None] if keepdims else streamed
     x, restore = _to_device(array)
     nd = x.ndim - 1
+    if x.shape[0] < nd:
+        raise IndexError(f"index {x.shape[0]} is out of bounds for axis 0 with size {x.shape[0]}")
+    ht = _traced_steps(step_size, nd, x.device)
+    if ht is not None:
+        acc = _check_and_return(accuracy, nd, "accuracy")
+        out = _run_traced(x, ht, [Term(0, k, k, 1, int(a), method, 1.0) for k, a in enumerate(acc)], 1)
+        return restore(out if keepdims else out.squeeze(0))
 
     def build():
         acc = _check_and_return(accuracy, nd, "accuracy")
@@ -460,8 +565,6 @@ def divergence(array, *, accuracy=1, step_size=1, keepdims: bool = True, method:
         return [Term(0, k, k, 1, int(a), method, _alpha(h, 1)) for k, (a, h) in enumerate(zip(acc, steps))]
 
     terms = _memo_terms("divergence", nd, accuracy, step_size, method, build)
-    if x.shape[0] < nd:
-        raise IndexError(f"index {x.shape[0]} is out of bounds for axis 0 with size {x.shape[0]}")
     out = _run(x, terms, 1)
     return restore(out if keepdims else out.squeeze(0))
 
@@ -540,6 +643,10 @@ def laplacian(array, *, accuracy=1, step_size=1, method: MethodKind = "central")
     if streamed is not None:
         return streamed
     x, restore = _to_device(array)
+    ht = _traced_steps(step_size, x.ndim, x.device)
+    if ht is not None:
+        acc = _check_and_return(accuracy, x.ndim, "accuracy")
+        return restore(_run_traced(x.unsqueeze(0), ht, [Term(0, 0, k, 2, int(a), method, 1.0) for k, a in enumerate(acc)], 1).squeeze(0))
 
     def build():
         acc = _check_and_return(accuracy, x.ndim, "accuracy")
@@ -562,10 +669,15 @@ def curl(array, *, accuracy=1, step_size=1, method: MethodKind = "central", keep
     x, restore = _to_device(array)
     nd = x.ndim - 1
     accuracy = _check_and_return(accuracy, nd, "accuracy")
-    step_size = _check_and_return(step_size, nd, "step_size")
+    ht = _traced_steps(step_size, nd, x.device) if nd >= 1 else None
+    if ht is None:
+        step_size = _check_and_return(step_size, nd, "step_size")
+        run = _run
+    else:
+        run = lambda xf, terms, n_out: _run_traced(xf, ht, terms, n_out)  # noqa: E731
 
     def term(co, ci, ax, sign):
-        return Term(co, ci, ax, 1, int(accuracy[ax]), method, sign * _alpha(step_size[ax], 1))
+        return Term(co, ci, ax, 1, int(accuracy[ax]), method, sign * (1.0 if ht is not None else _alpha(step_size[ax], 1)))
 
     if x.ndim == 4 and x.shape[0] == 3:
         terms = [
@@ -573,9 +685,9 @@ def curl(array, *, accuracy=1, step_size=1, method: MethodKind = "central", keep
             term(1, 0, 2, +1), term(1, 2, 0, -1),
             term(2, 1, 0, +1), term(2, 0, 1, -1),
         ]  # fmt: skip
-        return restore(_run(x, terms, 3))
+        return restore(run(x, terms, 3))
     if x.ndim == 3 and x.shape[0] == 2:
-        out = _run(x, [term(0, 1, 0, +1), term(0, 0, 1, -1)], 1)
+        out = run(x, [term(0, 1, 0, +1), term(0, 0, 1, -1)], 1)
         return restore(out if keepdims else out.squeeze(0))
     raise ValueError(
         f"`curl` is only implemented for 2D and 3D vector fields, got array.ndim={x.ndim}"

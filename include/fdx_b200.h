@@ -123,6 +123,25 @@ int fdx_curl3d_f32(const fdx_plan_t plans[3], const float* const x[3], float* co
 int fdx_curl3d_f64(const fdx_plan_t plans[3], const double* const x[3], double* const out[3],
                    const double alpha[3], const fdx_slab* slab, void* stream);
 
+/* ---- scale read on the device.  The reference traces `step_size` (finite_diff.py:168), so inside a jitted caller
+ * alpha = 1 / step_size**derivative is a DEVICE value; an XLA custom call must not fetch it.  `alpha_dev` is a device
+ * pointer to float64: one value for the axis operator (out = sign * alpha_dev[0] * D x), three (one per axis) for the
+ * 3-D operators.  These calls only enqueue kernels (no synchronisation, capture-safe).  The 3-D forms run as a
+ * composition of axis passes (the single-pass fused kernels fold alpha into their taps on the host); callers with
+ * concrete step sizes use the entry points above. */
+int fdx_axis_apply_dev_alpha_f32(fdx_plan_t plan, const float* x, float* out, int64_t outer, int64_t inner,
+                                 const double* alpha_dev, double sign, int accumulate, void* stream);
+int fdx_axis_apply_dev_alpha_f64(fdx_plan_t plan, const double* x, double* out, int64_t outer, int64_t inner,
+                                 const double* alpha_dev, double sign, int accumulate, void* stream);
+int fdx_laplacian3d_dev_alpha_f32(const fdx_plan_t plans[3], const float* x, float* out, const double* alpha_dev, void* stream);
+int fdx_laplacian3d_dev_alpha_f64(const fdx_plan_t plans[3], const double* x, double* out, const double* alpha_dev, void* stream);
+int fdx_divergence3d_dev_alpha_f32(const fdx_plan_t plans[3], const float* const x[3], float* out, const double* alpha_dev, void* stream);
+int fdx_divergence3d_dev_alpha_f64(const fdx_plan_t plans[3], const double* const x[3], double* out, const double* alpha_dev, void* stream);
+int fdx_gradient3d_dev_alpha_f32(const fdx_plan_t plans[3], const float* x, float* const out[3], const double* alpha_dev, void* stream);
+int fdx_gradient3d_dev_alpha_f64(const fdx_plan_t plans[3], const double* x, double* const out[3], const double* alpha_dev, void* stream);
+int fdx_curl3d_dev_alpha_f32(const fdx_plan_t plans[3], const float* const x[3], float* const out[3], const double* alpha_dev, void* stream);
+int fdx_curl3d_dev_alpha_f64(const fdx_plan_t plans[3], const double* const x[3], double* const out[3], const double* alpha_dev, void* stream);
+
 /* ---- introspection */
 int fdx_version(void);                 /* 1000*major + minor */
 const char* fdx_error_string(int code); /* static string for FDX_E* and cudaError_t values */

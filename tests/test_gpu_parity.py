@@ -543,3 +543,49 @@ def test_adjoints_through_every_march(dtype):
                 if dtype == torch.float64:
                     lhs, rhs = float((out * g).sum()), float((arr * ga).sum())
                     assert abs(lhs - rhs) <= 1e-10 * max(1.0, abs(lhs)), (op, shape, acc, lhs, rhs)
+
+
+# ------------------------------------------------------------------ traced step_size (device values)
+def test_step_size_as_a_device_value_needs_no_host_read_and_has_a_cotangent():
+    """The reference traces ``step_size`` (finite_diff.py:168): a CUDA-tensor step size must not be fetched by the host
+    (the call is captured in a CUDA graph here, where any host read raises) and ``grad`` w.r.t. it must be
+    -d / h * <g, term> summed over the terms of its axis."""
+    torch.manual_seed(12)
+    x = torch.randn(24, 28, 32, device="cuda", dtype=torch.float64)
+    f = torch.randn(3, 24, 28, 32, device="cuda", dtype=torch.float64)
+    hs = (0.1, 0.25, 0.4)
+    hd = torch.tensor(hs, device="cuda", dtype=torch.float64)
+    cases = [("laplacian", x, {}), ("gradient", x, {}), ("divergence", f, {"keepdims": False}), ("curl", f, {}), ("jacobian", f, {})]
+    for op, arr, kw in cases:
+        ref = getattr(fdx, op)(arr, accuracy=4, step_size=hs, **kw)
+        got = getattr(fdx, op)(arr, accuracy=4, step_size=tuple(hd[k] for k in range(3)), **kw)
+        assert torch.allclose(got, ref, rtol=1e-12, atol=1e-12 * ref.abs().max().item()), op
+    # one scalar device step for every axis, and `difference`
+    got = fdx.laplacian(x, accuracy=2, step_size=hd[0])
+    assert torch.allclose(got, fdx.laplacian(x, accuracy=2, step_size=0.1), rtol=1e-12, atol=1e-9)
+    got = fdx.difference(x, axis=1, accuracy=3, derivative=2, step_size=hd[1], method="forward")
+    assert torch.allclose(got, fdx.difference(x, axis=1, accuracy=3, derivative=2, step_size=0.25, method="forward"), rtol=1e-12, atol=1e-9)
+    # cotangent of the step sizes and of the array in one backward pass
+    h = hd.clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    out = fdx.laplacian(xr, accuracy=4, step_size=(h[0], h[1], h[2]))
+    g = torch.randn_like(out)
+    gx, gh = torch.autograd.grad(out, (xr, h), g)
+    (gx_ref,) = torch.autograd.grad(fdx.laplacian(xr, accuracy=4, step_size=hs), xr, g)
+    assert torch.allclose(gx, gx_ref, rtol=1e-11, atol=1e-11 * gx_ref.abs().max().item())
+    for k in range(3):
+        term = fdx.difference(x, axis=k, accuracy=4, derivative=2, step_size=hs[k])
+        want = -2.0 / hs[k] * float((g * term).sum())
+        assert abs(float(gh[k]) - want) <= 1e-10 * abs(want), (k, float(gh[k]), want)
+    # capture: a host read of the step size (.item(), .cpu()) would raise inside the capture
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fdx.gradient(x, accuracy=2, step_size=hd[2])  # warm-up: plans are created outside the capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            captured = fdx.gradient(x, accuracy=2, step_size=hd[2])
+    torch.cuda.current_stream().wait_stream(side)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(captured, fdx.gradient(x, accuracy=2, step_size=0.4), rtol=1e-12, atol=1e-9)
