@@ -16,6 +16,8 @@
 //       the leading CTAs of the two kernels above (one launch per call); axis_band is the same code as a
 //       kernel of its own behind the fallbacks.
 //   *_scalar     shape/alignment fallbacks of the above (still CUDA, never the host).
+#include <algorithm>
+
 #include "fdx_common.cuh"
 
 namespace fdx {
@@ -151,12 +153,15 @@ __global__ void __launch_bounds__(256) axis_row_kernel(const T* __restrict__ x, 
     band_element<T, ACC>(x, out, fb.n, fb.inner, fb.outer, fb.b, fb.alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, fb.alpha_dev);
     return;
   }
-  const int64_t g = ((int64_t)blockIdx.x - fb.blocks) * blockDim.x + threadIdx.x;
-  if (g >= total_vecs) return;
+  // a thread serves `vpt` output vectors, a whole grid of threads apart (coalesced, several independent windows in flight)
+  const int64_t nthreads = (int64_t)(gridDim.x - fb.blocks) * blockDim.x;
+  const T scale = dev_scale<T>(fb.alpha_dev);
+#pragma unroll 1
+  for (int64_t g = ((int64_t)blockIdx.x - fb.blocks) * blockDim.x + threadIdx.x; g < total_vecs; g += nthreads) {
   const int64_t row = g / n_v;
   const int t = (int)(g - row * n_v);
   const int i_first = t * V;
-  if (i_first + V <= r0 || i_first >= r1) return;  // band-only vector
+  if (i_first + V <= r0 || i_first >= r1) continue;  // band-only vector
   const T* xr = x + row * ((int64_t)n_v * V);
   constexpr int A = floor_div(LO, V), B = floor_div(V - 1 + HI, V), NV = B - A + 1, W = HI - LO + 1;
   T w[NV * V];
@@ -168,7 +173,6 @@ __global__ void __launch_bounds__(256) axis_row_kernel(const T* __restrict__ x, 
     for (int v = 0; v < V; ++v) w[u * V + v] = r.v[v];
   }
   Vec<T, V> res;
-  const T scale = dev_scale<T>(fb.alpha_dev);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     T acc = taps.c[0] * w[v + LO - A * V];
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(256) axis_row_kernel(const T* __restrict__ x, 
       const int i = i_first + v;
       if (i >= r0 && i < r1) orow[v] = ACC ? orow[v] + res.v[v] : res.v[v];
     }
+  }
   }
 }
 
@@ -239,11 +244,20 @@ static int launch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer,
   if (m <= 0) return FDX_OK;
   const int64_t inner_v = inner / V;
   const int64_t n_tiles = (inner_v + 127) / 128;
-  // enough CTAs for ~16 per SM, but chunks no shorter than 8 groups (halo re-read (W-1)/rows)
-  const int64_t want = (int64_t)kNumSMs * 16;
-  int64_t chunks = (want + n_tiles * outer - 1) / (n_tiles * outer);
+  // Rows per chunk: a chunk re-reads W - 1 halo rows, so long stencils want long chunks (B200 sweep of BASELINE
+  // config 2, tools/diff_probe.py: 7+ taps gain 4-9 % at ~220 rows, 3-5 taps are best at 24-60), but never fewer than
+  // ~4 CTAs per SM and never shorter than 8 groups.  FDX_AXIS_CPS = CTAs per SM instead (sweeps).
   const int min_rows = 8 * W;
-  int rows = (int)((m + chunks - 1) / chunks);
+  int rows;
+  if (const int cps = env_int("FDX_AXIS_CPS", 0)) {
+    const int64_t want = (int64_t)kNumSMs * std::max(1, cps);
+    const int64_t chunks = (want + n_tiles * outer - 1) / (n_tiles * outer);
+    rows = (int)((m + chunks - 1) / chunks);
+  } else {
+    const int64_t chunks_min = (4LL * kNumSMs + n_tiles * outer - 1) / (n_tiles * outer);
+    const int rows_max = (int)((m + chunks_min - 1) / chunks_min);
+    rows = std::min((W <= 5 ? 8 : 32) * W, rows_max);
+  }
   if (rows < min_rows) rows = min_rows;
   rows = ((rows + W - 1) / W) * W;
   if (rows > m) rows = m;
@@ -279,7 +293,11 @@ static int launch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, do
   const int n_v = p->n / V;
   const int64_t total = outer * n_v;
   const FusedBand<T> fb = fused_band<T>(p, outer, 1, alpha, 256, alpha_dev);
-  const int64_t blocks = (total + 255) / 256 + fb.blocks;
+  // vectors per thread (FDX_ROW_VPT): the index arithmetic of a thread is paid once, several windows are in flight
+  int vpt = env_int("FDX_ROW_VPT", 4);
+  if (vpt < 1) vpt = 1;
+  while (vpt > 1 && (total + 256LL * vpt - 1) / (256LL * vpt) < 4LL * kNumSMs) vpt /= 2;  // small arrays: keep the machine full
+  const int64_t blocks = (total + 256LL * vpt - 1) / (256LL * vpt) + fb.blocks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   axis_row_kernel<T, V, LO, HI, ACC><<<(unsigned)blocks, 256, 0, st>>>(x, out, total, n_v, p->nl, p->n - p->nr,
                                                                        scaled_taps<T>(p, alpha), fb);

@@ -1534,6 +1534,20 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
       FDX_CFG(10, 16, 16, 1, 8, 4, 8)  // one row per thread, 256 threads, 64 registers
       FDX_CFG(11, 32, 4, 2, 8, 4, 16)
       FDX_CFG(12, 16, 4, 2, 8, 8, 8)   // 64x8 tile, 64 threads, 8 CTAs per SM
+      // fp64 wide stencils (FDX_SWEEP_TSIZE=8 FDX_SWEEP_P=5): deeper rings, fewer / more CTAs per SM, narrow warps
+      FDX_CFG(13, 16, 8, 2, 6, 3)
+      FDX_CFG(14, 16, 8, 2, 7, 3)
+      FDX_CFG(15, 16, 8, 2, 5, 3)
+      FDX_CFG(16, 16, 8, 2, 6, 2)
+      FDX_CFG(17, 16, 8, 2, 4, 3, 8)
+      FDX_CFG(18, 32, 4, 2, 4, 3)
+      FDX_CFG(19, 16, 8, 2, 4, 2)
+      FDX_CFG(20, 16, 4, 2, 6, 5)
+      FDX_CFG(21, 16, 4, 2, 6, 6)
+      FDX_CFG(22, 8, 16, 2, 4, 3)
+      FDX_CFG(23, 16, 8, 2, 8, 2)
+      FDX_CFG(24, 16, 8, 2, 6, 5, 8)   // fp32: 5 CTAs per SM (96 registers)
+      FDX_CFG(25, 16, 8, 2, 5, 6, 8)   // fp32: 6 CTAs per SM (80 registers)
       default:
         break;
     }
