@@ -87,6 +87,12 @@ EXPORTS = (
     "fdx_gradient3d_dev_alpha_f64",
     "fdx_curl3d_dev_alpha_f32",
     "fdx_curl3d_dev_alpha_f64",
+    "fdx_laplacian2d_f32",
+    "fdx_laplacian2d_f64",
+    "fdx_divergence2d_f32",
+    "fdx_divergence2d_f64",
+    "fdx_gradient2d_f32",
+    "fdx_gradient2d_f64",
 )
 
 
@@ -113,6 +119,9 @@ def load():
         lib.fdx_plan_destroy.argtypes = [vp]
         for sfx in ("f32", "f64"):
             getattr(lib, f"fdx_axis_apply_{sfx}").argtypes = [vp, vp, vp, i64, i64, dbl, i32, vp]
+            getattr(lib, f"fdx_laplacian2d_{sfx}").argtypes = [C.POINTER(vp), vp, vp, C.POINTER(dbl), vp]
+            getattr(lib, f"fdx_divergence2d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(dbl), vp]
+            getattr(lib, f"fdx_gradient2d_{sfx}").argtypes = [C.POINTER(vp), vp, C.POINTER(vp), C.POINTER(dbl), vp]
             getattr(lib, f"fdx_axis_apply_dev_alpha_{sfx}").argtypes = [vp, vp, vp, i64, i64, vp, dbl, i32, vp]
             getattr(lib, f"fdx_laplacian3d_dev_alpha_{sfx}").argtypes = [C.POINTER(vp), vp, vp, vp, vp]
             getattr(lib, f"fdx_divergence3d_dev_alpha_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, vp, vp]
@@ -351,6 +360,44 @@ class FusedLauncher:
         rc = self.fn(self.hp, xin, xout, self.al, None, torch._C._cuda_getCurrentRawStream(self.dev_index))
         if rc != 0 and rc != -2:
             check(rc, f"fdx_{self.kind}3d")
+        return rc
+
+
+class FusedLauncher2D:
+    """Prepared launch of a fused 2-D operator (fdx_*2d_*): ``kind`` in laplacian / divergence / gradient; the field
+    indices say which input fields feed the axis-0 / axis-1 stencil and which output fields receive them (the 2-D curl
+    is a divergence of (F_1, F_0) with a negated second scale; its adjoint a gradient with swapped outputs)."""
+
+    __slots__ = ("kind", "plans", "keep", "hp", "al", "fn", "fin", "fout", "xin", "xout", "dev_index", "nout")
+
+    def __init__(self, kind: str, plans: Sequence[AxisPlan], alpha: Sequence[float], fin: Sequence[int], fout: Sequence[int], dtype: torch.dtype,
+                 device: torch.device):
+        sfx = "f32" if dtype == torch.float32 else "f64"
+        self.kind, self.plans = kind, tuple(plans)
+        self.keep = [device_plan(p, device) for p in plans]
+        self.hp = (C.c_void_p * 2)(*[dp.handle for dp in self.keep])
+        self.al = (C.c_double * 2)(*[float(a) for a in alpha])
+        self.fn = getattr(load(), f"fdx_{kind}2d_{sfx}")
+        self.fin, self.fout = tuple(fin), tuple(fout)
+        self.xin = (C.c_void_p * 2)() if kind == "divergence" else None
+        self.xout = (C.c_void_p * 2)() if kind == "gradient" else None
+        self.dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        self.nout = len(self.fout)
+
+    def launch(self, x_ptr: int, x_stride_bytes: int, out_ptr: int, out_stride_bytes: int) -> int:
+        if self.xin is None:
+            xin = x_ptr + self.fin[0] * x_stride_bytes
+        else:
+            xin = self.xin
+            xin[0], xin[1] = x_ptr + self.fin[0] * x_stride_bytes, x_ptr + self.fin[1] * x_stride_bytes
+        if self.xout is None:
+            xout = out_ptr + self.fout[0] * out_stride_bytes
+        else:
+            xout = self.xout
+            xout[0], xout[1] = out_ptr + self.fout[0] * out_stride_bytes, out_ptr + self.fout[1] * out_stride_bytes
+        rc = self.fn(self.hp, xin, xout, self.al, torch._C._cuda_getCurrentRawStream(self.dev_index))
+        if rc != 0 and rc != -2:
+            check(rc, f"fdx_{self.kind}2d")
         return rc
 
 

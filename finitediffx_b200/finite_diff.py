@@ -125,6 +125,56 @@ def _match_groups(terms: Sequence[Term], n_in: int, n_out: int, spatial):
     return None
 
 
+def _match_2d(terms: Sequence[Term]):
+    """Two terms on a 2-D grid, one per axis, as one fused 2-D launch: (kind, (t_axis0, t_axis1), input fields,
+    output fields) or None.  Same output and input: laplacian; same output, two inputs: divergence (the 2-D curl is one
+    with a negated scale); two outputs, same input: gradient (and the adjoints of the former two)."""
+    if len(terms) != 2 or {t.axis for t in terms} != {0, 1} or terms[0].transposed != terms[1].transposed:
+        return None
+    t0, t1 = sorted(terms, key=lambda t: t.axis)
+    if t0.co == t1.co:
+        if t0.ci == t1.ci:
+            return "laplacian", (t0, t1), (t0.ci,), (t0.co,)
+        return "divergence", (t0, t1), (t0.ci, t1.ci), (t0.co,)
+    if t0.ci == t1.ci:
+        return "gradient", (t0, t1), (t0.ci,), (t0.co, t1.co)
+    return None
+
+
+def _fused_lookup_2d(terms, n_in: int, n_out: int, spatial, dtype, device):
+    key = (id(terms), n_in, n_out, spatial, dtype, device.index)
+    hit = _fused_memo.get(key)
+    if hit is not None and hit[0] is terms:
+        return hit[1]
+    vkey = (terms, n_in, n_out, spatial, dtype, device.index, "2d")
+    hit = _fused_memo.get(vkey)
+    if hit is not None:
+        launcher = hit[1]
+    else:
+        # the whole list, or independent pairs grouped by input field (jacobian: one gradient per component) or by
+        # output field (its adjoint: one divergence per component)
+        groups = [terms] if len(terms) == 2 else []
+        if not groups and len(terms) % 2 == 0:
+            for attr in ("ci", "co"):
+                buckets: dict = {}
+                for t in terms:
+                    buckets.setdefault(getattr(t, attr), []).append(t)
+                if all(len(b) == 2 for b in buckets.values()):
+                    groups = [tuple(b) for b in buckets.values()]
+                    break
+        matches = [_match_2d(g) for g in groups]
+        launcher = None
+        if matches and all(m is not None for m in matches):
+            launcher = tuple(
+                _cabi.FusedLauncher2D(kind, (t0.plan(spatial[0]), t1.plan(spatial[1])), (t0.alpha, t1.alpha), fin, fout, dtype, device)
+                for kind, (t0, t1), fin, fout in matches)
+        if len(_fused_memo) > 512:
+            _fused_memo.clear()
+        _fused_memo[vkey] = (terms, launcher)
+    _fused_memo[key] = (terms, launcher)
+    return launcher
+
+
 def _fused_lookup(terms, n_in: int, n_out: int, spatial, dtype, device):
     """Memoised recognition of a term list as fused 3-D launches: a tuple of (prepared ``_cabi.FusedLauncher``, first
     input field, first output field) or None.  The key uses the identity of the term tuple (``_memo_terms`` hands out
@@ -159,6 +209,22 @@ def _execute(terms: Sequence[Term], x: torch.Tensor, n_out: int) -> torch.Tensor
     if x.numel() == 0:
         return out
     launches = _fused_lookup(terms, n_in, n_out, spatial, x.dtype, x.device) if len(spatial) == 3 else None
+    if len(spatial) == 2:
+        l2 = _fused_lookup_2d(terms, n_in, n_out, spatial, x.dtype, x.device)
+        if l2 is not None:
+            esz = x.element_size()
+            rc, done = 0, set()
+            with _cabi._on_device(x.device):
+                for one in l2:
+                    rc = one.launch(x.data_ptr(), x.stride(0) * esz, out.data_ptr(), out.stride(0) * esz)
+                    if rc != 0:
+                        break  # (not covered: everything goes through the axis kernels below)
+                    done.update(one.fout)
+            if rc == 0:
+                for co in range(n_out):
+                    if co not in done:
+                        out[co].zero_()
+                return out
     if launches is not None:
         esz = x.element_size()
         xs, os_ = x.stride(0) * esz, out.stride(0) * esz

@@ -123,6 +123,20 @@ int fdx_curl3d_f32(const fdx_plan_t plans[3], const float* const x[3], float* co
 int fdx_curl3d_f64(const fdx_plan_t plans[3], const double* const x[3], double* const out[3],
                    const double alpha[3], const fdx_slab* slab, void* stream);
 
+/* ---- fused 2-D operators on a C-contiguous (n0, n1) grid; plans[k] acts along axis k.  One pass: every input is read
+ * once, every output written once (the reference: two `difference` passes plus an add / stack, finite_diff.py:338-351,
+ * 443-453, 565-575, 586-606).  FDX_EUNSUPPORTED (use fdx_axis_apply) for stencil reach > 6, n1 not a multiple of the
+ * 16-byte vector, unaligned pointers and dense tiny-n plans.
+ *   laplacian : out = alpha[0] D_0 x + alpha[1] D_1 x
+ *   divergence: out = alpha[0] D_0 x[0] + alpha[1] D_1 x[1]      (2-D curl: x = {F_1, F_0}, alpha[1] negated)
+ *   gradient  : out[0] = alpha[0] D_0 x, out[1] = alpha[1] D_1 x  (with transposed plans: the adjoint of divergence) */
+int fdx_laplacian2d_f32(const fdx_plan_t plans[2], const float* x, float* out, const double alpha[2], void* stream);
+int fdx_laplacian2d_f64(const fdx_plan_t plans[2], const double* x, double* out, const double alpha[2], void* stream);
+int fdx_divergence2d_f32(const fdx_plan_t plans[2], const float* const x[2], float* out, const double alpha[2], void* stream);
+int fdx_divergence2d_f64(const fdx_plan_t plans[2], const double* const x[2], double* out, const double alpha[2], void* stream);
+int fdx_gradient2d_f32(const fdx_plan_t plans[2], const float* x, float* const out[2], const double alpha[2], void* stream);
+int fdx_gradient2d_f64(const fdx_plan_t plans[2], const double* x, double* const out[2], const double alpha[2], void* stream);
+
 /* ---- scale read on the device.  The reference traces `step_size` (finite_diff.py:168), so inside a jitted caller
  * alpha = 1 / step_size**derivative is a DEVICE value; an XLA custom call must not fetch it.  `alpha_dev` is a device
  * pointer to float64: one value for the axis operator (out = sign * alpha_dev[0] * D x), three (one per axis) for the

@@ -589,3 +589,86 @@ def test_step_size_as_a_device_value_needs_no_host_read_and_has_a_cotangent():
     graph.replay()
     torch.cuda.synchronize()
     assert torch.allclose(captured, fdx.gradient(x, accuracy=2, step_size=0.4), rtol=1e-12, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------- fused 2-D operators
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("method", O.METHODS)
+def test_fused_2d_operators(dtype, method):
+    """2-D laplacian / gradient / divergence / curl / jacobian run as ONE fused launch each (fdx_*2d_*): forward against
+    the oracle, vjp against the oracle's dense transposed matrices; grids around the vector / chunk sizes; per-axis
+    accuracy (zero-padded taps) included.  Most of the reference's own tests are 2-D (tests/test_finite_diff.py:161-307)."""
+    rng = np.random.default_rng(41)
+    tol = TOL[np.dtype(dtype)]
+    for shape in ((70, 96), (33, 64), (200, 24), (64, 260), (97, 132)):
+        x = rng.standard_normal(shape).astype(dtype)
+        f = rng.standard_normal((2,) + shape).astype(dtype)
+        f3 = rng.standard_normal((3,) + shape).astype(dtype)
+        cases = [("laplacian", x, dict(accuracy=4, step_size=(0.1, 0.3))), ("laplacian", x, dict(accuracy=(2, 6), step_size=0.5)),
+                 ("gradient", x, dict(accuracy=3, step_size=(0.1, 0.3))), ("divergence", f, dict(accuracy=2, step_size=(0.1, 0.3), keepdims=False)),
+                 ("divergence", f3, dict(accuracy=5, step_size=0.2)), ("curl", f, dict(accuracy=4, step_size=(0.1, 0.3))),
+                 ("jacobian", f3, dict(accuracy=2, step_size=(0.1, 0.3)))]
+        for op, arr, kw in cases:
+            kw = dict(kw, method=method)
+            acc = kw["accuracy"]
+            amax = max(acc) if isinstance(acc, tuple) else acc
+            d = 2 if op == "laplacian" else 1
+            if method != "central" and d + amax - 1 > 6:
+                continue  # reach > 6: the composition of axis kernels
+            if min(shape) < 2 * (d + amax):
+                continue
+            xt = _gpu(arr).requires_grad_(True)
+            out = getattr(fdx, op)(xt, **kw)
+            assert _cabi.last_kernel().startswith("fused_") and _cabi.last_kernel().endswith("2d"), (op, shape, kw, _cabi.last_kernel())
+            ref = getattr(O, op)(arr, **kw)
+            assert out.shape == ref.shape
+            err = parity_error(op, arr, kw, out.detach().cpu().numpy(), ref)
+            assert err <= tol, (op, shape, kw, err)
+            # vjp == oracle: flatten the operator through dense per-axis matrices
+            g = rng.standard_normal(ref.shape).astype(dtype)
+            (gx,) = torch.autograd.grad(out, xt, _gpu(g))
+            assert _cabi.last_kernel().endswith("2d"), (op, shape, kw, "vjp", _cabi.last_kernel())
+            hs = kw["step_size"] if isinstance(kw["step_size"], tuple) else (kw["step_size"],) * 2
+            accs = acc if isinstance(acc, tuple) else (acc,) * 2
+            D = [O.dense_matrix(shape[k], accuracy=accs[k], derivative=d, method=method, step_size=hs[k]) for k in range(2)]
+            ap = lambda k, a: np.moveaxis(np.tensordot(D[k].T, np.moveaxis(a, k, 0), axes=1), 0, k)  # noqa: E731
+            aa = lambda k, a: np.moveaxis(np.tensordot(np.abs(D[k].T), np.abs(np.moveaxis(a, k, 0)), axes=1), 0, k)  # noqa: E731
+            g64 = g.astype(np.float64)
+            if op == "laplacian":
+                want, sc = ap(0, g64) + ap(1, g64), aa(0, g64) + aa(1, g64)
+            elif op == "gradient":
+                want, sc = ap(0, g64[0]) + ap(1, g64[1]), aa(0, g64[0]) + aa(1, g64[1])
+            elif op == "divergence":
+                gg = g64[0] if g64.ndim == 3 else g64
+                want = np.stack([ap(0, gg), ap(1, gg)] + [np.zeros(shape)] * (arr.shape[0] - 2))
+                sc = np.stack([aa(0, gg), aa(1, gg)] + [np.ones(shape)] * (arr.shape[0] - 2))
+            elif op == "curl":  # out = D0 f1 - D1 f0
+                want, sc = np.stack([-ap(1, g64[0]), ap(0, g64[0])]), np.stack([aa(1, g64[0]), aa(0, g64[0])])
+            else:  # jacobian: out[c, k] = D_k f_c
+                want = np.stack([ap(0, g64[c, 0]) + ap(1, g64[c, 1]) for c in range(arr.shape[0])])
+                sc = np.stack([aa(0, g64[c, 0]) + aa(1, g64[c, 1]) for c in range(arr.shape[0])])
+            e2 = float(np.max(np.abs(gx.double().cpu().numpy() - want) / np.where(sc == 0, 1.0, sc)))
+            assert e2 <= tol, (op, shape, kw, "vjp", e2)
+
+
+def test_fused_2d_large_and_fallbacks():
+    """(2048, 2048) fp32 through the fused 2-D kernels against the oracle on strided rows / columns; grids the fused
+    kernels do not take (last axis not a multiple of the vector) fall back to the axis kernels with the same results."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((2048, 2048), device="cuda", generator=gen)
+    kw = dict(accuracy=4, step_size=(0.1, 0.2))
+    out = fdx.laplacian(x, **kw)
+    assert _cabi.last_kernel() == "fused_laplacian2d"
+    with _env(FDX_FUSED2D_DISABLE=1):
+        ref = fdx.laplacian(x, **kw)
+        assert _cabi.last_kernel() != "fused_laplacian2d"
+    assert ((out - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    cols = x[:, :64].cpu().numpy()  # full columns: the oracle's artificial edge is the right one, 24 columns away from the compared ones
+    oc = O.laplacian(cols, **kw)
+    s = sum(O.conditioning_scale(cols, axis=k, accuracy=4, derivative=2, method="central", step_size=kw["step_size"][k]) for k in range(2))
+    e = float(np.max(np.abs(out[:, :40].cpu().numpy().astype(np.float64) - oc[:, :40]) / s[:, :40]))
+    assert e <= 1e-5, e
+    xu = torch.randn((100, 97), device="cuda", generator=gen)  # 97 columns: not a multiple of 4
+    o2 = fdx.laplacian(xu, accuracy=2)
+    assert not _cabi.last_kernel().endswith("2d")
+    assert parity_error("laplacian", xu.cpu().numpy(), dict(accuracy=2), o2.cpu().numpy(), O.laplacian(xu.cpu().numpy(), accuracy=2)) <= 1e-5

@@ -20,6 +20,8 @@ for sp in sys.argv[1:]:
 keys = set(k for _, e in variants for k in e)
 x = torch.randn(8192, 8192, device="cuda")
 cases = [("central", 1, 2), ("central", 2, 4), ("central", 1, 6), ("central", 4, 8), ("forward", 1, 4), ("backward", 3, 8)]
+if os.environ.get("ALL_CASES"):  # the whole BASELINE config-2 sweep: only the medians are printed
+    cases = [(m, d, a) for m in ("central", "forward", "backward") for d in range(1, 5) for a in range(2, 9)]
 res = {}
 for rnd in range(3):
     for name, env in variants:
@@ -40,6 +42,13 @@ for rnd in range(3):
                 e1.record()
                 torch.cuda.synchronize()
                 res.setdefault((name, method, d, a, axis), []).append(e0.elapsed_time(e1) / 10)
+if os.environ.get("ALL_CASES"):
+    for name, _ in variants:
+        for axis in (0, 1):
+            v = sorted(statistics.median(res[(name, m, d, a, axis)]) for m, d, a in cases)
+            gb = lambda t: round(8192 * 8192 * 8 / t / 1e6)  # noqa: E731
+            print(name, f"axis {axis}: median {gb(v[len(v) // 2])} GB/s, best {gb(v[0])}, worst {gb(v[-1])}", flush=True)
+    sys.exit(0)
 for name, _ in variants:
     row = {}
     for method, d, a in cases:
