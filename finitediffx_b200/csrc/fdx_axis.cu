@@ -17,6 +17,7 @@
 //       kernel of its own behind the fallbacks.
 //   *_scalar     shape/alignment fallbacks of the above (still CUDA, never the host).
 #include <algorithm>
+#include <type_traits>
 
 #include "fdx_common.cuh"
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ void band_element(const T* __restrict__ x, T* __restr
 }
 
 // ------------------------------------------------------------------------------- axis_stream
-template <typename T, int V, int W, bool ACC>
+template <typename T, int V, int W, bool ACC, bool DEVA>
 __global__ void __launch_bounds__(128) axis_stream_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n,
                                                           int64_t inner_v, int lo, int r0, int r1, int rows_per_chunk,
                                                           int n_chunks, int64_t n_tiles, const __grid_constant__ Taps<T> taps,
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(128) axis_stream_kernel(const T* __restrict__ 
   T* op = out + (o * n + (int64_t)i0) * stride + jv * V;
 
   using VT = Vec<T, V>;
-  const T scale = dev_scale<T>(fb.alpha_dev);
+  T scale = 1;
+  if constexpr (DEVA) scale = dev_scale<T>(fb.alpha_dev);
   VT q[W];
 #pragma unroll
   for (int k = 0; k < W - 1; ++k) {
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(128) axis_stream_kernel(const T* __restrict__ 
       T acc = taps.c[0] * q[s % W].v[v];
 #pragma unroll
       for (int k = 1; k < W; ++k) acc = fma(taps.c[k], q[(s + k) % W].v[v], acc);
-      r.v[v] = fb.alpha_dev ? acc * scale : acc;
+      r.v[v] = DEVA ? acc * scale : acc;
     }
     if constexpr (ACC) {
       VT old = ld_cached<T, V>(op);
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(128) axis_stream_kernel(const T* __restrict__ 
 // ---------------------------------------------------------------------------------- axis_row
 __host__ __device__ constexpr int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <typename T, int V, int LO, int HI, bool ACC>
+template <typename T, int V, int LO, int HI, bool ACC, bool DEVA, bool LOOP>
 __global__ void __launch_bounds__(256) axis_row_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t total_vecs,
                                                        int n_v, int r0, int r1, const __grid_constant__ Taps<T> taps,
                                                        const __grid_constant__ FusedBand<T> fb) {
@@ -153,48 +155,58 @@ __global__ void __launch_bounds__(256) axis_row_kernel(const T* __restrict__ x, 
     band_element<T, ACC>(x, out, fb.n, fb.inner, fb.outer, fb.b, fb.alpha, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, fb.alpha_dev);
     return;
   }
-  // a thread serves `vpt` output vectors, a whole grid of threads apart (coalesced, several independent windows in flight)
-  const int64_t nthreads = (int64_t)(gridDim.x - fb.blocks) * blockDim.x;
-  const T scale = dev_scale<T>(fb.alpha_dev);
-#pragma unroll 1
-  for (int64_t g = ((int64_t)blockIdx.x - fb.blocks) * blockDim.x + threadIdx.x; g < total_vecs; g += nthreads) {
-  const int64_t row = g / n_v;
-  const int t = (int)(g - row * n_v);
-  const int i_first = t * V;
-  if (i_first + V <= r0 || i_first >= r1) continue;  // band-only vector
-  const T* xr = x + row * ((int64_t)n_v * V);
-  constexpr int A = floor_div(LO, V), B = floor_div(V - 1 + HI, V), NV = B - A + 1, W = HI - LO + 1;
-  T w[NV * V];
+  // LOOP: a thread serves several output vectors, a whole grid of threads apart (long stencils: the index arithmetic
+  // is paid once and several windows are in flight: the 11-13 tap cases of BASELINE config 2 gain 5 %); short stencils
+  // keep one vector per thread and straight-line code (the loop form measured 9-17 % slower at the median of the 84
+  // cases of an axis, with the same instructions inside: the early exits matter)
+  T scale = 1;
+  if constexpr (DEVA) scale = dev_scale<T>(fb.alpha_dev);
+  auto one = [&](int64_t g) {
+    const int64_t row = g / n_v;
+    const int t = (int)(g - row * n_v);
+    const int i_first = t * V;
+    if (i_first + V <= r0 || i_first >= r1) return;  // band-only vector
+    const T* xr = x + row * ((int64_t)n_v * V);
+    constexpr int A = floor_div(LO, V), B = floor_div(V - 1 + HI, V), NV = B - A + 1, W = HI - LO + 1;
+    T w[NV * V];
 #pragma unroll
-  for (int u = 0; u < NV; ++u) {
-    const int vi = min(max(t + A + u, 0), n_v - 1);
-    Vec<T, V> r = ld_cached<T, V>(xr + (int64_t)vi * V);
+    for (int u = 0; u < NV; ++u) {
+      const int vi = min(max(t + A + u, 0), n_v - 1);
+      Vec<T, V> r = ld_cached<T, V>(xr + (int64_t)vi * V);
 #pragma unroll
-    for (int v = 0; v < V; ++v) w[u * V + v] = r.v[v];
-  }
-  Vec<T, V> res;
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    T acc = taps.c[0] * w[v + LO - A * V];
-#pragma unroll
-    for (int k = 1; k < W; ++k) acc = fma(taps.c[k], w[v + LO + k - A * V], acc);
-    res.v[v] = fb.alpha_dev ? acc * scale : acc;
-  }
-  T* orow = out + row * ((int64_t)n_v * V) + i_first;
-  if (i_first >= r0 && i_first + V <= r1) {
-    if constexpr (ACC) {
-      Vec<T, V> old = ld_cached<T, V>(orow);
-#pragma unroll
-      for (int v = 0; v < V; ++v) res.v[v] += old.v[v];
+      for (int v = 0; v < V; ++v) w[u * V + v] = r.v[v];
     }
-    st_vec<T, V>(orow, res);
-  } else {
+    Vec<T, V> res;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const int i = i_first + v;
-      if (i >= r0 && i < r1) orow[v] = ACC ? orow[v] + res.v[v] : res.v[v];
+      T acc = taps.c[0] * w[v + LO - A * V];
+#pragma unroll
+      for (int k = 1; k < W; ++k) acc = fma(taps.c[k], w[v + LO + k - A * V], acc);
+      res.v[v] = DEVA ? acc * scale : acc;
     }
-  }
+    T* orow = out + row * ((int64_t)n_v * V) + i_first;
+    if (i_first >= r0 && i_first + V <= r1) {
+      if constexpr (ACC) {
+        Vec<T, V> old = ld_cached<T, V>(orow);
+#pragma unroll
+        for (int v = 0; v < V; ++v) res.v[v] += old.v[v];
+      }
+      st_vec<T, V>(orow, res);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int i = i_first + v;
+        if (i >= r0 && i < r1) orow[v] = ACC ? orow[v] + res.v[v] : res.v[v];
+      }
+    }
+  };
+  const int64_t g0 = ((int64_t)blockIdx.x - fb.blocks) * blockDim.x + threadIdx.x;
+  if constexpr (LOOP) {
+    const int64_t nthreads = (int64_t)(gridDim.x - fb.blocks) * blockDim.x;
+#pragma unroll 1
+    for (int64_t g = g0; g < total_vecs; g += nthreads) one(g);
+  } else {
+    if (g0 < total_vecs) one(g0);
   }
 }
 
@@ -265,8 +277,12 @@ static int launch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer,
   const FusedBand<T> fb = fused_band<T>(p, outer, inner, alpha, 128, alpha_dev);
   const int64_t blocks = n_tiles * n_chunks * outer + fb.blocks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
-  axis_stream_kernel<T, V, W, ACC><<<(unsigned)blocks, 128, 0, st>>>(x, out, p->n, inner_v, p->lo, r0, r1, rows, n_chunks,
-                                                                     n_tiles, scaled_taps<T>(p, alpha), fb);
+  if (alpha_dev)
+    axis_stream_kernel<T, V, W, ACC, true><<<(unsigned)blocks, 128, 0, st>>>(x, out, p->n, inner_v, p->lo, r0, r1, rows, n_chunks,
+                                                                             n_tiles, scaled_taps<T>(p, alpha), fb);
+  else
+    axis_stream_kernel<T, V, W, ACC, false><<<(unsigned)blocks, 128, 0, st>>>(x, out, p->n, inner_v, p->lo, r0, r1, rows, n_chunks,
+                                                                              n_tiles, scaled_taps<T>(p, alpha), fb);
   count_launch("axis_stream");
   *band_done = fb.blocks > 0;
   return FDX_OK;
@@ -293,14 +309,25 @@ static int launch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, do
   const int n_v = p->n / V;
   const int64_t total = outer * n_v;
   const FusedBand<T> fb = fused_band<T>(p, outer, 1, alpha, 256, alpha_dev);
-  // vectors per thread (FDX_ROW_VPT): the index arithmetic of a thread is paid once, several windows are in flight
-  int vpt = env_int("FDX_ROW_VPT", 4);
+  // vectors per thread (FDX_ROW_VPT; default 4 for stencils of 9+ taps, 1 below)
+  constexpr bool kLong = HI - LO + 1 >= 9;
+  int vpt = env_int("FDX_ROW_VPT", kLong ? 4 : 1);
   if (vpt < 1) vpt = 1;
   while (vpt > 1 && (total + 256LL * vpt - 1) / (256LL * vpt) < 4LL * kNumSMs) vpt /= 2;  // small arrays: keep the machine full
   const int64_t blocks = (total + 256LL * vpt - 1) / (256LL * vpt) + fb.blocks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
-  axis_row_kernel<T, V, LO, HI, ACC><<<(unsigned)blocks, 256, 0, st>>>(x, out, total, n_v, p->nl, p->n - p->nr,
-                                                                       scaled_taps<T>(p, alpha), fb);
+  auto go = [&](auto deva, auto loop) {
+    axis_row_kernel<T, V, LO, HI, ACC, decltype(deva)::value, decltype(loop)::value><<<(unsigned)blocks, 256, 0, st>>>(
+        x, out, total, n_v, p->nl, p->n - p->nr, scaled_taps<T>(p, alpha), fb);
+  };
+  using Tr = std::true_type;
+  using Fa = std::false_type;
+  if (alpha_dev)
+    go(Tr{}, Tr{});  // (the traced-scale path always takes the loop form: one instantiation)
+  else if (vpt > 1)
+    go(Fa{}, Tr{});
+  else
+    go(Fa{}, Fa{});
   count_launch("axis_row");
   *band_done = fb.blocks > 0;
   return FDX_OK;
