@@ -262,11 +262,11 @@ static int launch_stream(const fdx_plan_s* p, const T* x, T* out, int64_t outer,
   const int min_rows = 8 * W;
   int rows;
   if (const int cps = env_int("FDX_AXIS_CPS", 0)) {
-    const int64_t want = (int64_t)kNumSMs * std::max(1, cps);
+    const int64_t want = (int64_t)num_sms() * std::max(1, cps);
     const int64_t chunks = (want + n_tiles * outer - 1) / (n_tiles * outer);
     rows = (int)((m + chunks - 1) / chunks);
   } else {
-    const int64_t chunks_min = (4LL * kNumSMs + n_tiles * outer - 1) / (n_tiles * outer);
+    const int64_t chunks_min = (4LL * num_sms() + n_tiles * outer - 1) / (n_tiles * outer);
     const int rows_max = (int)((m + chunks_min - 1) / chunks_min);
     rows = std::min((W <= 5 ? 8 : 32) * W, rows_max);
   }
@@ -313,7 +313,7 @@ static int launch_row(const fdx_plan_s* p, const T* x, T* out, int64_t outer, do
   constexpr bool kLong = HI - LO + 1 >= 9;
   int vpt = env_int("FDX_ROW_VPT", kLong ? 4 : 1);
   if (vpt < 1) vpt = 1;
-  while (vpt > 1 && (total + 256LL * vpt - 1) / (256LL * vpt) < 4LL * kNumSMs) vpt /= 2;  // small arrays: keep the machine full
+  while (vpt > 1 && (total + 256LL * vpt - 1) / (256LL * vpt) < 4LL * num_sms()) vpt /= 2;  // small arrays: keep the machine full
   const int64_t blocks = (total + 256LL * vpt - 1) / (256LL * vpt) + fb.blocks;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   auto go = [&](auto deva, auto loop) {

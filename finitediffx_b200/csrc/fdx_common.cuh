@@ -21,7 +21,9 @@ struct fdx_plan_s {
 
 namespace fdx {
 
-constexpr int kNumSMs = 148;  // B200
+// Number of SMs of the current device (148 on B200), queried once per device: the chunk / grid sizing of every kernel
+// works in multiples of it.  (A build-time constant in round 1.)
+int num_sms();
 
 // Main taps travel by value in the kernel parameter block, pre-multiplied by alpha on the host in
 // float64 and rounded once to T, so the inner loops are FFMA/DFMA with constant-bank operands.

@@ -212,7 +212,7 @@ int launch2(const fdx_plan_s* const plans[2], const T* const in[2], T* const out
   prm.n_tiles = std::max(1, (vecs + 127) / 128);
   // rows per chunk as in axis_stream: long chunks for long stencils (W - 1 halo rows are re-read per chunk), but
   // at least ~4 CTAs per SM
-  const int64_t chunks_min = std::max<int64_t>(1, (4LL * kNumSMs + prm.n_tiles - 1) / prm.n_tiles);
+  const int64_t chunks_min = std::max<int64_t>(1, (4LL * num_sms() + prm.n_tiles - 1) / prm.n_tiles);
   int rpc = std::min((W <= 5 ? 8 : 32) * W, (int)((rows + chunks_min - 1) / chunks_min));
   rpc = std::max(rpc, std::min(rows, 8 * W));
   rpc = std::max(1, ((rpc + W - 1) / W) * W);

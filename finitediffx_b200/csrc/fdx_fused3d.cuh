@@ -1326,7 +1326,7 @@ static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans_in[3], co
   const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
   // rim tiles first only while a layer of tiles fits the machine (measured: +3 % at 512^3 = 256 tiles per layer,
   // -3 % at 1024^3 = 1024 tiles, where launching the rim apart from its neighbours costs L2 halo sharing)
-  prm.rim_first = env_int("FDX_FUSED_RIMFIRST", tiles <= (int64_t)kNumSMs * CFG::MINB ? 1 : 0);
+  prm.rim_first = env_int("FDX_FUSED_RIMFIRST", tiles <= (int64_t)num_sms() * CFG::MINB ? 1 : 0);
   // z chunking.  The planes next to a physical z boundary (one-sided taps, gathered directly) form
   // two chunks of their own, launched first, so that every other chunk is free of them and can take
   // the specialised march.  Every chunk pays 2P warm-up planes, so long chunks are cheaper, but the
@@ -1337,14 +1337,14 @@ static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans_in[3], co
     const int zlo_end = zsplit ? std::min(sl.z_end, std::max(sl.z_begin, plans[0]->nl)) : sl.z_begin;     // [z_begin, zlo_end): left band planes
     const int zhi_beg = zsplit ? std::max(zlo_end, std::min(sl.z_end, n0 - plans[0]->nr)) : sl.z_end;  // [zhi_beg, z_end): right band planes
     const int nz = zhi_beg - zlo_end;                                                     // planes of the graded middle part
-    const int64_t slots = (int64_t)kNumSMs * CFG::MINB;
+    const int64_t slots = (int64_t)num_sms() * CFG::MINB;
     int L = env_int("FDX_FUSED_CHUNK", 0), S = env_int("FDX_FUSED_CHUNK_SHORT", 0);
     const bool uniform = L > 0 && S <= 0;  // an explicit chunk alone means uniform chunks (sweeps)
     if (L <= 0) {
       // long chunks: 2P warm-up planes per chunk against the imbalance of long CTAs near the end of the launch.
       // L* = sqrt(2P nz tiles / (4 x 148)) fits the B200 sweeps (512^3: 40 at P = 3, 32 at P = 2; 1024^3: the cap)
       const int cap = 64 > 8 * P ? 64 : 8 * P;
-      const double lstar = std::sqrt(2.0 * P * (double)(nz > 0 ? nz : 1) * (double)tiles / (4.0 * kNumSMs));
+      const double lstar = std::sqrt(2.0 * P * (double)(nz > 0 ? nz : 1) * (double)tiles / (4.0 * num_sms()));
       L = ((int)(lstar + 2.0) / 4) * 4;
       if (L > cap) L = cap;
       if (L < 16) L = 16;
@@ -1487,12 +1487,12 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
   const int64_t blocks = (int64_t)prm.tiles_x * prm.tiles_y * prm.n_chunks;
   auto kern = fused3d_kernel<OP, T, P, CFG>;
   {
-    // once per kernel instantiation and device (the attribute is per device; 16 devices at most)
-    static std::atomic<unsigned> attr_done{0};
+    // once per kernel instantiation and device (the attribute is per device; ordinals beyond 63 set it at every launch)
+    static std::atomic<unsigned long long> attr_done{0};
     int dev = 0;
     cudaGetDevice(&dev);
-    const unsigned bit = 1u << (dev & 31);
-    if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (!bit || !(attr_done.load(std::memory_order_acquire) & bit)) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
       if (e != cudaSuccess) return (int)e;
       attr_done.fetch_or(bit, std::memory_order_release);

@@ -26,6 +26,18 @@ void count_launch(const char* family, int launches) {
   g_launches.fetch_add(launches, std::memory_order_relaxed);
 }
 
+int num_sms() {
+  static std::atomic<int> cache[64];  // per device ordinal; 0 = not queried yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 // ---- snapshot of the FDX_* environment switches
 using EnvTable = std::vector<std::pair<std::string, std::string>>;
 static std::mutex g_env_mu;
