@@ -90,6 +90,11 @@ struct AxisDev {
   int n, nl, wl, nr, wr;
   int tab_l, tab_r;   // offsets of the dense band taps inside FusedParams::tab
   int rng_l, rng_r;   // offsets of the per-row nonzero ranges inside FusedParams::rng
+  // head form of the bands (transposed plans, see corr_form()): a band row is the main stencil over the columns beyond
+  // the head plus a few dense taps on the first kcl / last kcr elements of the axis.  The tables at tab_l / tab_r then
+  // hold head[c][row] (alpha folded in): left rows 0 .. nlp-1, right rows n-nrp .. n-1 (nlp, nrp: nl, nr rounded up to
+  // a vector; rows that are not band rows carry zeros), right columns n-kcr .. n-1.
+  int corr, kcl, kcr, nlp, nrp;
   T alpha;            // scale applied on the band path
   T c[FDX_MAX_TAPS];  // main taps, pre-multiplied by alpha
 };
@@ -323,7 +328,9 @@ __host__ __device__ constexpr int out_lag(int o) {
   return (OP == LAP || OP == DIV) ? P : (OP == GRAD ? (o == 0 ? P : 0) : (o == 0 ? 0 : P));
 }
 
-template <Op OP, typename T, int P, typename CFG>
+// CORR: the instantiation that knows the head form of the bands (AxisDev::corr; launched when any axis has it:
+// the adjoints).  The plain instantiation carries none of that code, so the forward operators keep their registers.
+template <Op OP, typename T, int P, typename CFG, bool CORR>
 __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     fused3d_kernel(const __grid_constant__ FusedParams<T, P> prm) {
   using G = Geometry<OP, T, P, CFG>;
@@ -401,17 +408,24 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   const bool yedge = (y0 < prm.ax[1].nl) || (y0 + G::TY > n1 - prm.ax[1].nr);
   const bool edge = xedge_l || xedge_r || yedge;
   // per-plane flags of this CTA's march, one byte each: the loop reads them instead of re-deriving them
-  enum : uint32_t { F_INR = 1, F_EMIT = 2, F_ZB = 4, F_SLOW = 8 };
+  // (z axis in head form: the band planes leave the queue like every other plane -- planes outside the grid count
+  // as zero, head planes are kept out of the queue -- and receive their head taps when they are emitted: F_EZB;
+  // no direct gathers, no F_ZB)
+  enum : uint32_t { F_INR = 1, F_EMIT = 2, F_ZB = 4, F_SLOW = 8, F_EZB = 16 };
+  const bool zcorr = CORR && prm.ax[0].corr != 0;
   for (int i = tid; i < n_planes; i += G::NT) {
     const int z = zin0 + i, zo = z - P;
     const bool inr = z >= zs && z < ze;                                             // an output plane of ours
-    const bool zb = inr && (z < prm.ax[0].nl || z >= n0 - prm.ax[0].nr);            // next to a physical z boundary
-    const bool emit = zo >= zs && !(zo < prm.ax[0].nl || zo >= n0 - prm.ax[0].nr);  // plane z - P leaves the queue
-    const uint32_t f = (inr ? F_INR : 0u) | (emit ? F_EMIT : 0u) | (zb ? F_ZB : 0u) | ((inr && (edge || zb)) ? F_SLOW : 0u);
+    const bool zb = !zcorr && inr && (z < prm.ax[0].nl || z >= n0 - prm.ax[0].nr);  // next to a physical z boundary
+    const bool zbo = zo < prm.ax[0].nl || zo >= n0 - prm.ax[0].nr;
+    const bool emit = zo >= zs && (zcorr || !zbo);                                  // plane z - P leaves the queue
+    const uint32_t f = (inr ? F_INR : 0u) | (emit ? F_EMIT : 0u) | (zb ? F_ZB : 0u) | ((inr && (edge || zb)) ? F_SLOW : 0u) |
+                       ((CORR && emit && zbo) ? F_EZB : 0u);
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(flag_base + (uint32_t)i), "r"(f) : "memory");
   }
-  if (xedge_l || xedge_r) {  // the dense x-band rows (left, then right) go to shared memory
-    const int cnt = prm.ax[2].nl * prm.ax[2].wl + prm.ax[2].nr * prm.ax[2].wr;  // <= xtab_max(P), host-checked
+  if (xedge_l || xedge_r) {  // the dense x-band rows (left, then right) or the x head tables go to shared memory
+    const int cnt = (CORR && prm.ax[2].corr) ? prm.ax[2].kcl * prm.ax[2].nlp + prm.ax[2].kcr * prm.ax[2].nrp
+                                   : prm.ax[2].nl * prm.ax[2].wl + prm.ax[2].nr * prm.ax[2].wr;  // <= xtab_max(P), host-checked
     for (int i = tid; i < cnt; i += G::NT) {
       const T c = prm.tab[prm.ax[2].tab_l + i];
       if constexpr (sizeof(T) == 4)
@@ -461,6 +475,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   const AxisDev<T>& A0 = prm.ax[0];
   const AxisDev<T>& A1 = prm.ax[1];
   const AxisDev<T>& A2 = prm.ax[2];
+  const bool xcorr = CORR && A2.corr != 0, ycorr = CORR && A1.corr != 0;  // (constants in the plain instantiation)
   const int plane = n1 * n2;  // < 2^31, host-checked
   // n2 % V == 0, so a vector is entirely in or out of the grid
   // row j of this thread lies inside the grid: bit j (opaque, so that it stays one register)
@@ -493,10 +508,43 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     }
   const int plane_b = plane * (int)sizeof(T);  // < 2^31, host-checked
 
+  // Bands in head form (CORR instantiation, AxisDev::corr): the main stencil of a band row must not see the head
+  // elements of its axis (the first kcl / last kcr: they enter through the head table instead).  Every output that a
+  // head element reaches through the main stencil is a band row (host-checked: kc + P <= nl), so the elements are
+  // simply hidden from the main path -- bit j of xmask: entry j of this thread's x window is a head column; bit i of
+  // ymask: centre row i of its y march is a head row (thread constants); along z the head planes skip the queue.
+  constexpr int XW = (2 * HXV + 1) * V;
+  uint32_t xmask = 0, ymask = 0;
+  if constexpr (CORR) {
+    if (xcorr) {
+#pragma unroll
+      for (int j = 0; j < XW; ++j) {
+        const int col = xg - HX + j;
+        if ((col >= 0 && col < A2.kcl) || (col >= n2 - A2.kcr && col < n2)) xmask |= 1u << j;
+      }
+    }
+    if (ycorr) {
+#pragma unroll
+      for (int i = 0; i < RY + 2 * P; ++i) {
+        const int row = yg - P + i;
+        if ((row >= 0 && row < A1.kcl) || (row >= n1 - A1.kcr && row < n1)) ymask |= 1u << i;
+      }
+    }
+    asm volatile("" : "+r"(xmask), "+r"(ymask));
+  }
+
   // ------------------------------------------------------------------ hot in-plane helpers
   // D_y, streaming: centre row i of the RY+2P rows a thread sees feeds output rows j = i-2P .. i
   // with tap i-j, so only one centre row is live at a time (keeps the register footprint small)
-  auto dy_feed = [&](VT (&ys)[RY], const VT& ci, int i) {  // i is a constant after unrolling
+  // (mk: a constant at every call site -- the copies of the march that serve tiles with band rows apply the masks)
+  auto dy_feed = [&](VT (&ys)[RY], const VT& ci_in, int i, bool mk) {  // i is a constant after unrolling
+    VT ci = ci_in;
+    if constexpr (CORR) {
+      if (mk && ((ymask >> i) & 1u)) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) ci.v[v] = 0;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < RY; ++j) {
       const int k = i - j;
@@ -511,9 +559,50 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // that owns the band columns of a side replaces them: band row v is the dot product of its taps
   // xcl[t][v] / xcr[t][v] (prm.xfast layout) with the window it already holds, taps in ascending column
   // order like the reference's sum.  The host guarantees that the window reaches far enough (prm.xdirect).
+  auto lds_s = [&](uint32_t a) {
+    T r;
+    if constexpr (sizeof(T) == 4)
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+    else
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
+    return r;
+  };
+  // x bands in head form (A2.corr): the band rows inside this thread's vector receive their head taps -- the first /
+  // last columns of the grid row -- on top of the main stencil, which ran with those columns masked (xmask).  What
+  // depends on the thread only is computed once: xc_kc columns (0: no band row of either side in this vector -- a
+  // vector never holds band rows of both, corr_form()), xc_xoff = bytes from the thread's vector to the first of
+  // those columns inside a tile row, xc_tab = shared address of its first coefficient vector (tables at `xtab`: left
+  // block, then right block).  Columns in ascending order; the rim copy and the generic march share the code (same bits).
+  int xc_kc = 0, xc_xoff = 0;
+  uint32_t xc_tab = 0;
+  if (xcorr) {
+    if (xedge_l && xg < A2.nl) {
+      xc_kc = A2.kcl, xc_xoff = -xg * (int)sizeof(T), xc_tab = xtab + (uint32_t)(xg * (int)sizeof(T));
+    } else if (xedge_r && xg + V > n2 - A2.nr && xg < n2) {
+      xc_kc = A2.kcr, xc_xoff = (n2 - A2.kcr - xg) * (int)sizeof(T);
+      xc_tab = xtab + (uint32_t)((A2.kcl * A2.nlp + (xg - (n2 - A2.nrp))) * (int)sizeof(T));
+    }
+  }
+  // xs[j] += sum_c head[c][.] * x[row j][c]; row0 = shared address of this thread's vector in the row of yg
+  auto xcorr_apply = [&](uint32_t row0, int pitch_b, VT (&xs)[RY]) {
+    if (xc_kc == 0) return;
+    const uint32_t tpitch = (uint32_t)((xg < A2.nl ? A2.nlp : A2.nrp) * (int)sizeof(T));
+    uint32_t xa_ = row0 + (uint32_t)xc_xoff, ca = xc_tab;
+#pragma unroll 1
+    for (int c = xc_kc; c > 0; --c) {
+      const VT cf = lds_vec<T, V>(ca);
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        const T xv = lds_s(xa_ + (uint32_t)(j * pitch_b));
+#pragma unroll
+        for (int v = 0; v < V; ++v) xs[j].v[v] = fma(cf.v[v], xv, xs[j].v[v]);
+      }
+      xa_ += (uint32_t)sizeof(T), ca += tpitch;
+    }
+  };
   const bool xdir = prm.xdirect && !(prm.dbg & 2);
   const bool own_l = xedge_l && tx == 0 && xdir, own_r = xedge_r && tx == (n2 - V - x0) / V && xdir;
-  auto dx_main = [&](uint32_t row, const VT& centre, bool xb) {
+  auto dx_main = [&](uint32_t row, const VT& centre, bool xb, bool mk) {
     constexpr int W = (2 * HXV + 1) * V;
     T w[W];
 #pragma unroll
@@ -528,6 +617,13 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) w[HXV * V + v] = centre.v[v];
+    if constexpr (CORR) {
+      if (mk && xmask) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+          if ((xmask >> j) & 1u) w[j] = 0;
+      }
+    }
     VT r;
     if constexpr (sizeof(T) == 4) {
       // outputs (0,1) and (2,3): tap k of output v reads w[HX + v - P + k].  When that index is even for the first
@@ -561,7 +657,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
         r.v[v] = s;
       }
     }
-    if (xb) {
+    if (xb && !xcorr) {
       constexpr int XT = FusedParams<T, P>::kXT;
       if (own_l) {
         T val[V];
@@ -683,14 +779,6 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   // (right) band output and all of its taps.  `row0` = shared address of tile column 0 of the tile
   // row that holds grid row y0 of this field.
   constexpr int NB = 32 / WR;  // band columns per pass
-  auto lds_s = [&](uint32_t a) {
-    T r;
-    if constexpr (sizeof(T) == 4)
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
-    else
-      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
-    return r;
-  };
   auto xband_coop = [&](uint32_t row0, int pitch, VT (&xs)[RY]) {
     const int r = lane % WR, bl = lane / WR;
     const uint32_t rowa = row0 + (uint32_t)(((ty / TRW) * WR + r) * pitch * (int)sizeof(T));
@@ -804,6 +892,50 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     return a;
   };
   auto is_yband = [&](int j) { return rok(j) && (yg + j < A1.nl || yg + j >= n1 - A1.nr); };
+  // y / z bands in head form: band row y (plane z) = the main stencil over the rows beyond the head (already in `acc`)
+  // + the head taps on the first / last rows (planes) of the axis, ascending.  `load(c)` returns this thread's vector of row (plane) c0 + c.
+  auto corr_rows = [&](const AxisDev<T>& A, int i, T sgn, VT& acc, auto load /* (int global row or plane) -> VT */, auto batched) {
+    const bool left = i < A.nl;
+    const int kc = left ? A.kcl : A.kcr, pitch = left ? A.nlp : A.nrp;
+    const int c0 = left ? 0 : A.n - A.kcr;
+    int ti = left ? A.tab_l + i : A.tab_r + (i - (A.n - A.nrp));
+    if constexpr (decltype(batched)::value) {
+      // four rows per batch, their loads issued together (the z form gathers from L2: one round trip per batch); a row
+      // past the last one repeats it with a zero factor, so that every element of the batch is defined
+#pragma unroll 1
+      for (int c = 0; c < kc; c += 4) {
+        T cf[4];
+        VT x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int cu = min(u, kc - 1 - c);
+          cf[u] = (c + u < kc) ? sgn * prm.tab[ti + cu * pitch] : (T)0;
+          x[u] = load(c0 + c + cu);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc.v[v] = fma(cf[u], x[u].v[v], acc.v[v]);
+        ti += 4 * pitch;
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < kc; ++c) {
+        const T cf = sgn * prm.tab[ti];
+        const VT x = load(c0 + c);
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc.v[v] = fma(cf, x.v[v], acc.v[v]);
+        ti += pitch;
+      }
+    }
+  };
+  // ... y, rows from the tile (tcol: shared address of (tile row 0, this thread's x) of the field)
+  auto ycorr_tile = [&](uint32_t tcol, int pitch_b, int y, VT& acc) {
+    corr_rows(A1, y, (T)1, acc, [&](int row) { return lds_vec<T, V>(tcol + (uint32_t)((row - (y0 - P)) * pitch_b)); }, std::false_type{});
+  };
+  // does the tile hold the head rows of its band rows?  (first / last tile row; uniform per CTA)
+  const bool ycorr_ok = ycorr && (!(y0 < A1.nl) || (y0 <= P && A1.kcl <= y0 + G::TY + P)) &&
+                        (!(y0 + G::TY > n1 - A1.nr) || (n1 - A1.kcr >= y0 - P && n1 <= y0 + G::TY + P));
   auto store = [&](int o, int z, int j, const VT& val) {
     if (rok(j)) stg_vec<T, V>(ob[o][j] + (uint64_t)((int64_t)z * (int64_t)plane_b), val);
   };
@@ -830,16 +962,16 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
 
   // ---------------- pieces of one march step (shared by the generic and the specialised loop)
   // hot: loads of plane zc and its in-plane taps
-  auto hot_inplane = [&](VT (&zv)[Tr::NACC][RY], VT (&ya)[NY][RY], VT (&xa)[NX][RY], bool xb) {
+  auto hot_inplane = [&](VT (&zv)[Tr::NACC][RY], VT (&ya)[NY][RY], VT (&xa)[NX][RY], bool xb, bool mk) {
     if constexpr (OP == LAP || OP == GRAD) {
 #pragma unroll
       for (int i = 0; i < RY + 2 * P; ++i) {
         const uint32_t row = tb[0] + soff + (uint32_t)(i * G::box_x(0) * sizeof(T));
         const VT ci = lds_vec<T, V>(row);
-        dy_feed(ya[0], ci, i);
+        dy_feed(ya[0], ci, i, mk);
         if (i >= P && i < P + RY) {
           zv[0][i - P] = ci;
-          xa[0][i - P] = dx_main(row, ci, xb);
+          xa[0][i - P] = dx_main(row, ci, xb, mk);
         }
       }
     } else if constexpr (OP == DIV) {
@@ -847,31 +979,31 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       for (int j = 0; j < RY; ++j) zv[0][j] = lds_vec<T, V>(tb[0] + soff + (uint32_t)(j * G::box_x(0) * sizeof(T)));
 #pragma unroll
       for (int i = 0; i < RY + 2 * P; ++i)
-        dy_feed(ya[0], lds_vec<T, V>(tb[1] + soff + (uint32_t)(i * G::box_x(1) * sizeof(T))), i);
+        dy_feed(ya[0], lds_vec<T, V>(tb[1] + soff + (uint32_t)(i * G::box_x(1) * sizeof(T))), i, mk);
 #pragma unroll
       for (int j = 0; j < RY; ++j) {
         const uint32_t row = tb[2] + soff + (uint32_t)(j * G::box_x(2) * sizeof(T));
-        xa[0][j] = dx_main(row, lds_vec<T, V>(row), xb);
+        xa[0][j] = dx_main(row, lds_vec<T, V>(row), xb, mk);
       }
     } else {  // CURL
 #pragma unroll
       for (int i = 0; i < RY + 2 * P; ++i) {
         const VT ci = lds_vec<T, V>(tb[2] + soff + (uint32_t)(i * G::box_x(2) * sizeof(T)));
-        dy_feed(ya[0], ci, i);                        // D1 x2
+        dy_feed(ya[0], ci, i, mk);                    // D1 x2
         if (i >= P && i < P + RY) zv[0][i - P] = ci;  // x2 -> -D0 x2 into out_1
       }
 #pragma unroll
       for (int j = 0; j < RY; ++j) {
         const uint32_t row = tb[1] + soff + (uint32_t)(j * G::box_x(1) * sizeof(T));
         zv[1][j] = lds_vec<T, V>(row);      // x1 -> +D0 x1 into out_2
-        xa[0][j] = dx_main(row, zv[1][j], xb);  // D2 x1
+        xa[0][j] = dx_main(row, zv[1][j], xb, mk);  // D2 x1
       }
 #pragma unroll
       for (int i = 0; i < RY + 2 * P; ++i) {
         const uint32_t row = tb[0] + soff + (uint32_t)(i * G::box_x(0) * sizeof(T));
         const VT ci = lds_vec<T, V>(row);
-        dy_feed(ya[1], ci, i);                                       // D1 x0
-        if (i >= P && i < P + RY) xa[1][i - P] = dx_main(row, ci, xb);  // D2 x0
+        dy_feed(ya[1], ci, i, mk);                                   // D1 x0
+        if (i >= P && i < P + RY) xa[1][i - P] = dx_main(row, ci, xb, mk);  // D2 x0
       }
     }
   };
@@ -959,8 +1091,8 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   const bool ytile_ok = prm.ydirect && (!(y0 < A1.nl) || (y0 <= P && A1.wl <= y0 + G::TY + P)) &&
                         (!(y0 + G::TY > n1 - A1.nr) || (n1 - A1.wr >= y0 - P && n1 <= y0 + G::TY + P));
   const bool fast_ok = prm.plain_ok && (x0 + G::TX <= x_hi) && (x_lo == x0) && (y0 + G::TY <= n1) && zs >= A0.nl && ze <= n0 - A0.nr &&
-                       n_planes == nout + 2 * P && (!(xedge_l || xedge_r) || prm.xdirect || (prm.dbg & 48)) &&
-                       (!yedge || ytile_ok || (prm.dbg & 16));
+                       n_planes == nout + 2 * P && (!(xedge_l || xedge_r) || prm.xdirect || xcorr || (prm.dbg & 48)) &&
+                       (!yedge || (ycorr ? ycorr_ok : ytile_ok) || (prm.dbg & 16));
   if (fast_ok) {
     uint64_t oz[Tr::NOUT][RY];
 #pragma unroll
@@ -981,7 +1113,14 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       VT zv[Tr::NACC][RY], tin[Tr::NACC][RY], eo[Tr::NACC][RY];
       if (inr) {
         VT ya[NY][RY], xa[NX][RY], ip[NIP + 1][RY];
-        hot_inplane(zv, ya, xa, xe);
+        hot_inplane(zv, ya, xa, xe, be);
+        if (xe && xcorr && !(prm.dbg & 64)) {
+#pragma unroll
+          for (int qq = 0; qq < NX; ++qq) {
+            const int f = IP::xfield(qq);
+            xcorr_apply(tb[f] + soff + (uint32_t)(G::yoff(f) * G::box_x(f) * sizeof(T)), G::box_x(f) * (int)sizeof(T), xa[qq]);
+          }
+        }
         if (ye) {
           if (yband && !(prm.dbg & 4)) {
 #pragma unroll
@@ -991,7 +1130,13 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
               const uint32_t tcol = tb[f] + soff - (uint32_t)(ty * RY * G::box_x(f) * (int)sizeof(T));
 #pragma unroll
               for (int j = 0; j < RY; ++j)
-                if (is_yband(j)) ya[qq][j] = band_y_tile(tcol, G::box_x(f) * (int)sizeof(T), yg + j);
+                if (is_yband(j)) {
+                  if (ycorr) {
+                    if (!(prm.dbg & 128)) ycorr_tile(tcol, G::box_x(f) * (int)sizeof(T), yg + j, ya[qq][j]);
+                  }
+                  else
+                    ya[qq][j] = band_y_tile(tcol, G::box_x(f) * (int)sizeof(T), yg + j);
+                }
             }
           }
         }
@@ -1042,6 +1187,21 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(f) : "r"(flag_base + (uint32_t)i));
     return f;
   };
+  // z bands in head form: output plane zo (a band plane, just completed by the queue) receives its head taps on
+  // the first / last planes of the grid, gathered from global memory (L2: those planes were just streamed)
+  auto zcorr_emit = [&](int zo, VT (&eo)[Tr::NACC][RY]) {
+#pragma unroll
+    for (int a = 0; a < Tr::NACC; ++a) {
+      const int f = OP == CURL ? (a == 0 ? 2 : 1) : 0;                 // LAP / DIV / GRAD: D0 of field 0; CURL: -D0 x2, +D0 x1
+      const T sgn = (OP == CURL && a == 0) ? (T)-1 : (T)1;
+#pragma unroll
+      for (int j = 0; j < RY; ++j) {
+        if (!rok(j)) continue;
+        const T* gcol0 = prm.in[f] + thread_ofs + (int64_t)j * n2;
+        corr_rows(A0, zo, sgn, eo[a][j], [&](int pl) { return ld_cached<T, V>(gcol0 + (int64_t)pl * plane); }, std::true_type{});
+      }
+    }
+  };
   uint32_t fl_next = lds_flag(0);
   for (int it = 0; it < n_planes; ++it, ++zc) {
     const uint32_t fl = fl_next;
@@ -1057,7 +1217,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     VT tin[Tr::NACC][RY];  // in-plane contribution to output plane zc of each accumulator set
     if (inr) {
       VT ya[NY][RY], xa[NX][RY];  // raw in-plane derivatives of plane zc
-      hot_inplane(zv, ya, xa, false);
+      hot_inplane(zv, ya, xa, false, true);
       // ---------------- cold: rows / columns next to a physical boundary of the grid
       if (slow && edge) {
         const int64_t zofs = (int64_t)zc * plane;
@@ -1068,15 +1228,27 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
             const int f = IP::yfield(qq);
 #pragma unroll
             for (int j = 0; j < RY; ++j)
-              if (is_yband(j))
-                ya[qq][j] = band_y(tile(f) + G::xoff(f) + tx * V, G::box_x(f), G::box_y(f), prm.in[f] + zofs + xg, yg + j, false);
+              if (is_yband(j)) {
+                if (ycorr) {
+                  if (ycorr_ok) {  // (the same loads as the rim copy)
+                    ycorr_tile(tb[f] + soff - (uint32_t)(ty * RY * G::box_x(f) * (int)sizeof(T)), G::box_x(f) * (int)sizeof(T), yg + j, ya[qq][j]);
+                  } else {
+                    const T* gcol = prm.in[f] + zofs + xg;
+                    corr_rows(A1, yg + j, (T)1, ya[qq][j], [&](int row) { return ld_cached<T, V>(gcol + (int64_t)row * n2); }, std::true_type{});
+                  }
+                } else {
+                  ya[qq][j] = band_y(tile(f) + G::xoff(f) + tx * V, G::box_x(f), G::box_y(f), prm.in[f] + zofs + xg, yg + j, false);
+                }
+              }
           }
         }
         if (xedge_l || xedge_r) {
 #pragma unroll
           for (int qq = 0; qq < NX; ++qq) {
             const int f = IP::xfield(qq);
-            if (xfast) {
+            if (xcorr) {
+              xcorr_apply(tb[f] + soff + (uint32_t)(G::yoff(f) * G::box_x(f) * sizeof(T)), G::box_x(f) * (int)sizeof(T), xa[qq]);
+            } else if (xfast) {
               xband_fast(tb[f] + soff + (uint32_t)(G::yoff(f) * G::box_x(f) * sizeof(T)), G::box_x(f), xa[qq]);
             } else {
               xband_coop(ring + soff + G::field_off(f) + (uint32_t)(G::yoff(f) * G::box_x(f) * sizeof(T)), G::box_x(f), xa[qq]);
@@ -1117,15 +1289,52 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       zonly_loads(zv);
     }
     release();
+    if constexpr (CORR) {
+      if (zcorr && (zc < A0.kcl || zc >= n0 - A0.kcr)) {  // a head plane reaches its outputs through the head table only
+#pragma unroll
+        for (int a = 0; a < Tr::NACC; ++a)
+#pragma unroll
+          for (int j = 0; j < RY; ++j)
+#pragma unroll
+            for (int v = 0; v < V; ++v) zv[a][j].v[v] = 0;
+      }
+    }
     VT eo[Tr::NACC][RY];
     ztaps(zv, emit, eo);
     if (emit) {
+      if constexpr (CORR) {
+        if (fl & F_EZB) zcorr_emit(zc - P, eo);
+      }
 #pragma unroll
       for (int a = 0; a < Tr::NACC; ++a)
 #pragma unroll
         for (int j = 0; j < RY; ++j) store(OP == CURL ? a + 1 : 0, zc - P, j, eo[a][j]);
     }
     if (inr && !zb) join(tin);
+  }
+  if (zcorr) {
+    // the last P planes of the grid leave the queue behind the last input plane: the planes beyond the grid are zero
+    for (int zo = max(zs, zin1 - P + 1); zo < ze; ++zo) {
+      VT eo[Tr::NACC][RY];
+#pragma unroll
+      for (int a = 0; a < Tr::NACC; ++a) {
+#pragma unroll
+        for (int j = 0; j < RY; ++j) eo[a][j] = q[a][2 * P - 1][j];
+#pragma unroll
+        for (int i = 2 * P - 1; i >= 1; --i)
+#pragma unroll
+          for (int j = 0; j < RY; ++j) q[a][i][j] = q[a][i - 1][j];
+#pragma unroll
+        for (int j = 0; j < RY; ++j)
+#pragma unroll
+          for (int v = 0; v < V; ++v) q[a][0][j].v[v] = 0;
+      }
+      zcorr_emit(zo, eo);
+#pragma unroll
+      for (int a = 0; a < Tr::NACC; ++a)
+#pragma unroll
+        for (int j = 0; j < RY; ++j) store(OP == CURL ? a + 1 : 0, zo, j, eo[a][j]);
+    }
   }
 }
 
@@ -1217,10 +1426,48 @@ static bool pad_plan(PaddedPlan& out, const fdx_plan_s* src, int P) {
   return true;
 }
 
+// Head form of a plan's bands.  A TRANSPOSED plan (the adjoints: P + L band rows of up to 2L + 1 taps) differs from the
+// radius-P main stencil only on its first / last few columns -- the columns that belong to the forward plan's one-sided
+// rows: band row r = [main stencil over the columns beyond the head] + sum over the kc head columns of band[r][c] x[c].
+// The kernel evaluates it that way: the main path runs on the band rows too, with the head elements hidden from it
+// (masks; elements outside the grid are zero fill anyway), and a kc-tap head table adds the rest -- the same products
+// as the dense row, tail first.  x-edge tiles stay on the specialised march, z-band planes gather kc planes instead of
+// up to 2L + 1.  The reference's forward plans (one-sided rows: as wide as the rows) keep the dense form.
+// Conditions: every row that reaches a head column through the main stencil is a band row (kc + P <= nl, so that
+// hiding the head from the main path changes no main row), and the dense rows do not extend past the main stencil's
+// reach.  main / band are compared as T values scaled by alpha, so that rows that merely repeat the main stencil
+// (pad_plan) count as equal.  kcl / kcr: columns [0, kcl) and [n - kcr, n) form the heads.
+template <typename T>
+static bool corr_form(const fdx_plan_s* p, int P, double alpha, int& kcl, int& kcr) {
+  kcl = kcr = 0;
+  if (env_int("FDX_FUSED_NOCORR", 0)) return false;
+  auto main_t = [&](int o) { return (o >= p->lo && o <= p->hi && o >= -P && o <= P) ? (T)(p->main_taps[o - p->lo] * alpha) : (T)0; };
+  for (int r = 0; r < p->nl; ++r)
+    for (int c = 0; c < p->wl; ++c)
+      if ((T)(p->h_band_l[r * p->wl + c] * alpha) != main_t(c - r)) kcl = std::max(kcl, c + 1);
+  for (int r = 0; r < p->nr; ++r)
+    for (int c = 0; c < p->wr; ++c)
+      if ((T)(p->h_band_r[r * p->wr + c] * alpha) != main_t((c - p->wr) - (r - p->nr))) kcr = std::max(kcr, p->wr - c);
+  // the main stencil of row r reaches columns r - P .. r + P, the dense row covers [0, wl): beyond it the main stencil
+  // must have no taps
+  for (int r = 0; r < p->nl; ++r)
+    for (int o = -P; o <= P; ++o)
+      if (r + o >= p->wl && main_t(o) != (T)0) return false;
+  for (int r = 0; r < p->nr; ++r)  // row n - nr + r, dense columns [n - wr, n)
+    for (int o = -P; o <= P; ++o)
+      if ((p->n - p->nr + r) + o < p->n - p->wr && main_t(o) != (T)0) return false;
+  const int kmax = std::max(kcl, kcr), wmax = std::max(p->wl, p->wr);
+  if (kmax == 0) return false;
+  constexpr int V = 16 / (int)sizeof(T);
+  const int nlp = ((p->nl + V - 1) / V) * V, nrp = ((p->nr + V - 1) / V) * V;
+  if (kcl + P > p->nl || kcr + P > p->nr) return false;
+  return kmax <= 8 && 2 * kmax <= wmax && nlp + nrp <= p->n;
+}
+
 // Everything of a launch that does not depend on the data pointers: band tables, x-band layouts, tile counts, the
 // list of z chunks.  Cached per (plans, alpha, slab) by launch_cfg.  prm.n_chunks == 0 on return: nothing to do.
 template <Op OP, typename T, int P, typename CFG>
-static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans_in[3], const double alpha[3], const SlabArgs& sl) {
+static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans_in[3], const double alpha[3], const SlabArgs& sl, bool allow_corr) {
   using G = Geometry<OP, T, P, CFG>;
   PaddedPlan padded[3];
   const fdx_plan_s* plans[3];
@@ -1240,6 +1487,23 @@ static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans_in[3], co
     for (int t = 0; t < FDX_MAX_TAPS; ++t) {  // tap t of the kernel sits at offset t - P; the plan's taps cover lo .. hi
       const int o = t - P;
       a.c[t] = (t < 2 * P + 1 && o >= p->lo && o <= p->hi) ? (T)(p->main_taps[o - p->lo] * alpha[k]) : (T)0;
+    }
+    a.corr = (allow_corr && corr_form<T>(p, P, alpha[k], a.kcl, a.kcr)) ? 1 : 0;
+    a.nlp = ((p->nl + G::V - 1) / G::V) * G::V, a.nrp = ((p->nr + G::V - 1) / G::V) * G::V;
+    if (a.corr) {
+      // head[c][row] tables, alpha folded in: left rows 0 .. nlp - 1 and columns 0 .. kcl - 1, right rows n - nrp .. n - 1
+      // and columns n - kcr .. n - 1 (rows that are not band rows: zeros)
+      if (tab_used + a.kcl * a.nlp + a.kcr * a.nrp > tab_max(P)) return FDX_EUNSUPPORTED;
+      a.tab_l = tab_used, a.rng_l = a.rng_r = 0;
+      for (int c = 0; c < a.kcl; ++c)
+        for (int r = 0; r < a.nlp; ++r) prm.tab[tab_used++] = (r < p->nl && c < p->wl) ? (T)(p->h_band_l[r * p->wl + c] * alpha[k]) : (T)0;
+      a.tab_r = tab_used;
+      for (int c = 0; c < a.kcr; ++c)      // global column n - kcr + c
+        for (int r = 0; r < a.nrp; ++r) {  // global row n - nrp + r
+          const int br = r - (a.nrp - p->nr), bc = p->wr - a.kcr + c;  // row / column inside the dense right band
+          prm.tab[tab_used++] = (br >= 0 && bc >= 0) ? (T)(p->h_band_r[br * p->wr + bc] * alpha[k]) : (T)0;
+        }
+      continue;
     }
     for (int side = 0; side < 2; ++side) {
       const int rows = side ? p->nr : p->nl, w = side ? p->wr : p->wl;
@@ -1317,7 +1581,8 @@ static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans_in[3], co
     const fdx_plan_s* px = plans[2];
     const int xl = n2 > G::TX ? n2 - G::TX : 0;  // origin of the (shifted) last tile
     if (px->nl > G::TX || px->wl > G::TX + G::HX || n2 - xl < px->nr || xl > n2 - px->wr + G::HX) return FDX_EUNSUPPORTED;
-    if (px->nl * px->wl + px->nr * px->wr > xtab_max(P)) return FDX_EUNSUPPORTED;
+    if ((prm.ax[2].corr ? prm.ax[2].kcl * prm.ax[2].nlp + prm.ax[2].kcr * prm.ax[2].nrp : px->nl * px->wl + px->nr * px->wr) > xtab_max(P))
+      return FDX_EUNSUPPORTED;
     if (prm.tiles_x == 2) {  // the cut between the first tile and the shifted second one (see the kernel): the right band
       const int cut = std::min(G::TX, std::max(xl, ((px->nl + G::V - 1) / G::V) * G::V));  // must lie behind it
       if (n2 - px->nr < cut) return FDX_EUNSUPPORTED;
@@ -1426,7 +1691,9 @@ static int build_params(FusedParams<T, P>& prm, const fdx_plan_t plans_in[3], co
   return FDX_OK;
 }
 
-template <Op OP, typename T, int P, typename CFG>
+// ALLOW_CORR: this tile configuration also exists as the CORR instantiation of the kernel (the default configurations
+// only: the alternates of the sweeps and the wide-band shape keep the dense bands, and the build its size)
+template <Op OP, typename T, int P, typename CFG, bool ALLOW_CORR = false>
 static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const out[3], const double alpha[3],
                       const SlabArgs& sl, cudaStream_t st) {
   using G = Geometry<OP, T, P, CFG>;
@@ -1465,7 +1732,7 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
       e.epoch = epoch;
       for (int k = 0; k < 3; ++k) e.p[k] = plans[k], e.a[k] = alpha[k];
       e.sl = sl;
-      e.rc = build_params<OP, T, P, CFG>(e.prm, plans, alpha, sl);
+      e.rc = build_params<OP, T, P, CFG>(e.prm, plans, alpha, sl, ALLOW_CORR);
       hit = &e;
     }
     rc = hit->rc;
@@ -1485,10 +1752,9 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
     if (rc2) return rc2;
   }
   const int64_t blocks = (int64_t)prm.tiles_x * prm.tiles_y * prm.n_chunks;
-  auto kern = fused3d_kernel<OP, T, P, CFG>;
-  {
+  const bool corr = ALLOW_CORR && (prm.ax[0].corr | prm.ax[1].corr | prm.ax[2].corr) != 0;
+  auto go = [&](auto kern, std::atomic<unsigned long long>& attr_done) -> int {
     // once per kernel instantiation and device (the attribute is per device; ordinals beyond 63 set it at every launch)
-    static std::atomic<unsigned long long> attr_done{0};
     int dev = 0;
     cudaGetDevice(&dev);
     const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
@@ -1497,8 +1763,16 @@ static int launch_cfg(const fdx_plan_t plans[3], const T* const in[3], T* const 
       if (e != cudaSuccess) return (int)e;
       attr_done.fetch_or(bit, std::memory_order_release);
     }
-  }
-  kern<<<(unsigned)blocks, G::NT, G::SMEM_BYTES, st>>>(prm);
+    kern<<<(unsigned)blocks, G::NT, G::SMEM_BYTES, st>>>(prm);
+    return FDX_OK;
+  };
+  static std::atomic<unsigned long long> attr_plain{0}, attr_corr{0};
+  int rc_l;
+  if constexpr (ALLOW_CORR)
+    rc_l = corr ? go(fused3d_kernel<OP, T, P, CFG, true>, attr_corr) : go(fused3d_kernel<OP, T, P, CFG, false>, attr_plain);
+  else
+    rc_l = go(fused3d_kernel<OP, T, P, CFG, false>, attr_plain);
+  if (rc_l != FDX_OK) return rc_l;
   count_launch(OP == LAP ? "fused_laplacian3d" : OP == DIV ? "fused_divergence3d" : OP == GRAD ? "fused_gradient3d" : "fused_curl3d");
   FDX_LAUNCH_CHECK();
   return FDX_OK;
@@ -1548,6 +1822,11 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
       FDX_CFG(23, 16, 8, 2, 8, 2)
       FDX_CFG(24, 16, 8, 2, 6, 5, 8)   // fp32: 5 CTAs per SM (96 registers)
       FDX_CFG(25, 16, 8, 2, 5, 6, 8)   // fp32: 6 CTAs per SM (80 registers)
+      // fp64 wide stencils, four rows per thread (14 row loads per 4 vectors instead of 12 per 2): 160 queue registers
+      FDX_CFG(26, 16, 8, 4, 4, 2)      // 64x32 tile, 128 threads, 2 CTAs per SM
+      FDX_CFG(27, 16, 4, 4, 3, 4)      // 64x16 tile, 64 threads, 4 CTAs per SM
+      FDX_CFG(28, 16, 8, 4, 3, 2)
+      FDX_CFG(29, 16, 4, 4, 4, 3)
       default:
         break;
     }
@@ -1561,23 +1840,29 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
       FDX_CFG(1, 16, 8, 2, 4, 3)
       default:
         // two register queues: from radius 4 on they need more than 128 registers
-        return launch_cfg<OP, T, P, Cfg<16, 16, 1, 4, (P <= 3 ? 2 : 1)>>(plans, in, out, alpha, sl, st);
+        return launch_cfg<OP, T, P, Cfg<16, 16, 1, 4, (P <= 3 ? 2 : 1)>, true>(plans, in, out, alpha, sl, st);
     }
   } else if constexpr (OP == LAP && sizeof(T) == 4 && P <= 3) {
     // wide x bands (transposed plans: P + L band columns) go through the warp-cooperative path, whose cost per warp
     // grows with the rows a warp covers: full-width warps (LX = 16, 4 rows) halve it
-    const bool wide = plans[2]->nl > 16 / (int)sizeof(T) || plans[2]->nr > 16 / (int)sizeof(T);
+    // (bands in head form cost the same at any width: they keep the default shape)
+    bool wide = plans[2]->nl > 16 / (int)sizeof(T) || plans[2]->nr > 16 / (int)sizeof(T);
+    if (wide) {
+      PaddedPlan pp;
+      int kl, kr;
+      if (pad_plan(pp, plans[2], P) && corr_form<T>(&pp.p, P, alpha[2], kl, kr)) wide = false;
+    }
     switch (cfg == 0 && wide && !env_int("FDX_FUSED_NOWIDECFG", 0) ? 2 : cfg) {
       FDX_CFG(1, 16, 8, 2, 4, 3)
       FDX_CFG(2, 16, 8, 2, 8, 4, 16)
       default:
-        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 8, 4, 8>>(plans, in, out, alpha, sl, st);
+        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 8, 4, 8>, true>(plans, in, out, alpha, sl, st);
     }
   } else {
     switch (cfg) {
       FDX_CFG(1, 16, 16, 1, 4, 2)
       default:
-        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 4, 3>>(plans, in, out, alpha, sl, st);
+        return launch_cfg<OP, T, P, Cfg<16, 8, 2, 4, 3>, true>(plans, in, out, alpha, sl, st);
     }
   }
 #undef FDX_CFG
