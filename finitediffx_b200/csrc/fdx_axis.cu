@@ -23,6 +23,10 @@
 
 namespace fdx {
 
+// fdx_rowtma.cu: the contiguous axis of big aligned arrays (FDX_EUNSUPPORTED: not its case)
+template <typename T>
+int row_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done);
+
 // ---------------------------------------------------------------------------------- band rows
 // The few boundary rows with their own dense taps.  One element per thread; `g` numbers the band elements of the
 // whole array.  Runs as the leading CTAs of the main kernels (FusedBand: one launch per call, the band rows'
@@ -365,7 +369,12 @@ static int apply_impl(const fdx_plan_s* p, const T* x, T* out, int64_t outer, in
         rc = dispatch_stream<T, 1, ACC>(p, x, out, outer, inner, alpha, st, &band_done, alpha_dev);
     } else {
       rc = FDX_EUNSUPPORTED;
-      if (aligned16 && p->n % V == 0) rc = dispatch_row<T, V, ACC>(p, x, out, outer, alpha, st, &band_done, alpha_dev);
+      // big arrays: the persistent TMA-staged row kernel (fdx_rowtma.cu); it writes, so not for the accumulating form
+      if constexpr (!ACC) {
+        if (!alpha_dev) rc = row_tma_apply<T>(p, x, out, outer, alpha, st, &band_done);
+      }
+      if (rc == FDX_EUNSUPPORTED && aligned16 && p->n % V == 0)
+        rc = dispatch_row<T, V, ACC>(p, x, out, outer, alpha, st, &band_done, alpha_dev);
       if (rc == FDX_EUNSUPPORTED) {
         const int64_t total = outer * m;
         const int64_t blocks = (total + 255) / 256;

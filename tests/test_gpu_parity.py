@@ -672,3 +672,27 @@ def test_fused_2d_large_and_fallbacks():
     o2 = fdx.laplacian(xu, accuracy=2)
     assert not _cabi.last_kernel().endswith("2d")
     assert parity_error("laplacian", xu.cpu().numpy(), dict(accuracy=2), o2.cpu().numpy(), O.laplacian(xu.cpu().numpy(), accuracy=2)) <= 1e-5
+
+
+# ------------------------------------------------------------------ contiguous axis of big arrays: the TMA row kernel
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_row_tma_kernel_equals_axis_row_bit_for_bit_and_the_oracle(dtype):
+    """`difference` along the last axis of big arrays runs the persistent TMA-staged row kernel (fdx_rowtma.cu).  Forced
+    onto small awkward shapes (partial last strip, partial last row block, 3-D outer, one row) it must equal the L1-gather
+    kernel bit for bit (same fma chains) and meet the parity bound against the oracle, for all three methods."""
+    rng = np.random.default_rng(21)
+    v = 4 if dtype == np.float32 else 2
+    for shape in ((37, 129 * v), (8, 250 * v), (3, 5, 160 * v), (1, 128 * v), (19, 128 * v + v)):
+        x = rng.standard_normal(shape).astype(dtype)
+        for method, d, a in (("central", 1, 2), ("central", 2, 4), ("central", 1, 8), ("central", 4, 8), ("forward", 1, 1), ("forward", 2, 5),
+                             ("forward", 4, 8), ("backward", 1, 3), ("backward", 3, 8)):
+            kw = dict(axis=-1, accuracy=a, derivative=d, method=method, step_size=0.37)
+            with _env(FDX_ROWTMA_MIN_MB=0):
+                out = _call("difference", x, **kw)
+                assert _cabi.last_kernel() == "axis_rowtma", (shape, method, d, a, _cabi.last_kernel())
+            with _env(FDX_ROWTMA_DISABLE=1):
+                other = _call("difference", x, **kw)
+                assert _cabi.last_kernel().startswith("axis_row"), _cabi.last_kernel()
+            assert np.array_equal(out, other), (shape, method, d, a, float(np.abs(out - other).max()))
+            err = parity_error("difference", x, kw, out, O.difference(x, **kw))
+            assert err <= TOL[np.dtype(dtype)], (shape, method, d, a, err)
