@@ -23,7 +23,9 @@
 
 namespace fdx {
 
-// fdx_rowtma.cu: the contiguous axis of big aligned arrays (FDX_EUNSUPPORTED: not its case)
+// fdx_rowtma.cu / fdx_coltma.cu: the contiguous axis / a strided axis of big aligned arrays (FDX_EUNSUPPORTED: not their case)
+template <typename T>
+int col_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, cudaStream_t st, bool* band_done);
 template <typename T>
 int row_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done);
 
@@ -363,7 +365,13 @@ static int apply_impl(const fdx_plan_s* p, const T* x, T* out, int64_t outer, in
   bool band_done = false;  // the band rows rode along with the main kernel
   if (m > 0) {
     if (inner > 1) {
-      if (aligned16 && inner % V == 0)
+      rc = FDX_EUNSUPPORTED;
+      // big arrays: the persistent TMA-staged kernel for strided axes (fdx_coltma.cu); it writes, so not for the accumulating form
+      if constexpr (!ACC) {
+        if (!alpha_dev) rc = col_tma_apply<T>(p, x, out, outer, inner, alpha, st, &band_done);
+      }
+      if (rc != FDX_EUNSUPPORTED) {
+      } else if (aligned16 && inner % V == 0)
         rc = dispatch_stream<T, V, ACC>(p, x, out, outer, inner, alpha, st, &band_done, alpha_dev);
       else
         rc = dispatch_stream<T, 1, ACC>(p, x, out, outer, inner, alpha, st, &band_done, alpha_dev);

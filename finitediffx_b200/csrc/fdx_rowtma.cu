@@ -15,65 +15,15 @@
 // The band columns (one-sided stencils next to the two ends of the axis) are computed by a sixth warp of the same CTAs,
 // one element per lane, with the arithmetic of the other axis kernels (band_element).  Per output the taps are summed in
 // ascending order with the same fma chain as axis_row: the two kernels agree bit for bit.
-#include <cuda.h>
-
 #include <algorithm>
-#include <atomic>
-#include <mutex>
 
-#include "fdx_common.cuh"
+#define FDX_TMA_DEFINE_CLAIM_SLOT
+#include "fdx_tma.cuh"
 
 namespace fdx {
 
 namespace rowtma {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-               "l"(map), "r"(bar), "r"(c0), "r"(c1)
-               : "memory");
-}
-template <typename T, int V>
-__device__ __forceinline__ Vec<T, V> lds_vec(uint32_t addr) {
-  Vec<T, V> r;
-  if constexpr (sizeof(T) == 4)
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(addr));
-  else
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(addr));
-  return r;
-}
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long p, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
-}
-
-__host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+using namespace tma;
 
 template <typename T, int LO, int HI>
 struct Geo {
@@ -264,49 +214,6 @@ __global__ void __launch_bounds__(192, 5) axis_rowtma_kernel(const __grid_consta
     if (lane == 0) mbar_arrive(bar_empty + 8u * stage);
     if (++stage == STAGES) stage = 0, parity ^= 1u;
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  });
-  return fn;
-}
-
-// Counter pairs for the item claims, per device: kSlots pairs handed out round-robin, each rewound to zero by the grid
-// that used it (launches on one stream are ordered; more than kSlots launches in flight on different streams would
-// share a pair).  Allocated and zeroed at the first use on a device -- not while the stream is being captured.
-static unsigned int* claim_slot(cudaStream_t st) {
-  constexpr int kSlots = 256, kDevs = 64;
-  static unsigned int* pool[kDevs] = {nullptr};
-  static std::atomic<unsigned> next{0};
-  static std::mutex mu;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kDevs) return nullptr;
-  unsigned int* base;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    base = pool[dev];
-    if (!base) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
-      if (cudaMalloc(&base, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-      if (cudaMemset(base, 0, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) {
-        cudaFree(base);
-        return nullptr;
-      }
-      pool[dev] = base;
-    }
-  }
-  return base + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kSlots);
 }
 
 template <typename T, int LO, int HI>

@@ -225,7 +225,7 @@ def test_config2_all_168_cases_8192_squared():
                     assert err <= 1e-5, (method, d, a, axis, err, _cabi.last_kernel())
                     cases += 1
     assert cases == 168
-    assert kernels <= {"axis_stream", "axis_row", "axis_rowtma"}, kernels  # the vector kernels, never a scalar fallback
+    assert kernels <= {"axis_stream", "axis_row", "axis_rowtma", "axis_coltma"}, kernels  # the vector kernels, never a scalar fallback
     print(f"config 2: 168 cases, worst parity error {worst:.2e}")
 
 

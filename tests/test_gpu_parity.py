@@ -696,3 +696,28 @@ def test_row_tma_kernel_equals_axis_row_bit_for_bit_and_the_oracle(dtype):
             assert np.array_equal(out, other), (shape, method, d, a, float(np.abs(out - other).max()))
             err = parity_error("difference", x, kw, out, O.difference(x, **kw))
             assert err <= TOL[np.dtype(dtype)], (shape, method, d, a, err)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_col_tma_kernel_equals_axis_stream_bit_for_bit_and_the_oracle(dtype):
+    """`difference` along a strided axis of big arrays runs the persistent TMA-staged kernel of fdx_coltma.cu.  Forced onto
+    small awkward shapes (partial last strip, partial last row block, outer > 1, axis length below one row block) it must
+    equal axis_stream bit for bit (same fma chains) and meet the parity bound against the oracle, for all three methods."""
+    rng = np.random.default_rng(22)
+    v = 4 if dtype == np.float32 else 2
+    for shape, axis in (((70, 33 * v), 0), ((3, 50, 40 * v), 1), ((2, 3, 45, 32 * v), 2), ((41, 5, 32 * v), 0), ((20, 64 * v + v), 0)):
+        x = rng.standard_normal(shape).astype(dtype)
+        for method, d, a in (("central", 1, 2), ("central", 2, 4), ("central", 1, 8), ("central", 4, 8), ("forward", 1, 1), ("forward", 2, 5),
+                             ("forward", 4, 8), ("backward", 1, 3), ("backward", 3, 8)):
+            if 2 * (d + a) > shape[axis]:  # the reference rejects axes shorter than its three row regions
+                continue
+            kw = dict(axis=axis, accuracy=a, derivative=d, method=method, step_size=0.37)
+            with _env(FDX_COLTMA_MIN_MB=0):
+                out = _call("difference", x, **kw)
+                assert _cabi.last_kernel() == "axis_coltma", (shape, method, d, a, _cabi.last_kernel())
+            with _env(FDX_COLTMA_DISABLE=1):
+                other = _call("difference", x, **kw)
+                assert _cabi.last_kernel() == "axis_stream", _cabi.last_kernel()
+            assert np.array_equal(out, other), (shape, axis, method, d, a, float(np.abs(out - other).max()))
+            err = parity_error("difference", x, kw, out, O.difference(x, **kw))
+            assert err <= TOL[np.dtype(dtype)], (shape, axis, method, d, a, err)
