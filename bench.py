@@ -594,7 +594,9 @@ def _extras_single(fdx, _cabi, dev, peak):
         for d in range(1, 5):
             for a in range(2, 9):
                 for axis in (0, 1):
-                    t = timed(lambda v: fdx.difference(v, axis=axis, accuracy=a, derivative=d, method=method, step_size=0.5), [x], k=10, wu=3)
+                    # (best of two runs of 10 calls: a host hiccup inside a 1 ms timed region would otherwise pass for a slow case)
+                    call = lambda v: fdx.difference(v, axis=axis, accuracy=a, derivative=d, method=method, step_size=0.5)  # noqa: E731
+                    t = min(timed(call, [x], k=10, wu=3), timed(call, [x], k=10, wu=1))
                     per_axis[axis].append((t, method, d, a))
     pts = 8192 * 8192
     for axis, rows in per_axis.items():
@@ -605,7 +607,7 @@ def _extras_single(fdx, _cabi, dev, peak):
             "median": _entry(pts, 8, med[0], peak),
             "best": _entry(pts, 8, best[0], peak, case=list(best[1:])),
             "worst": _entry(pts, 8, worst[0], peak, case=list(worst[1:])),
-            "note": "per call through the public API (host launch path included)",
+            "note": "per call through the public API (host launch path included); per case the better of two runs of 10 calls",
         }
     del x
     torch.cuda.empty_cache()

@@ -81,7 +81,7 @@ inline EncodeTiledFn encode_fn() {
 
 // Counter pairs for the item claims, per device: kSlots pairs handed out round-robin, each rewound to zero by the grid
 // that used it (launches on one stream are ordered; more than kSlots launches in flight on different streams would
-// share a pair).  Allocated and zeroed at the first use on a device -- not while the stream is being captured.
+// share a pair).  Allocated and zeroed at the first use on a device.
 unsigned int* claim_slot(cudaStream_t st);  // fdx_rowtma.cu
 #ifdef FDX_TMA_DEFINE_CLAIM_SLOT
 unsigned int* claim_slot(cudaStream_t st) {
@@ -91,13 +91,15 @@ unsigned int* claim_slot(cudaStream_t st) {
   static std::mutex mu;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kDevs) return nullptr;
+  // never inside a stream capture: a captured launch would keep its pair for every replay of the graph, next to eager
+  // launches that are handed the same pair later (the caller then takes the non-persistent kernel)
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
   unsigned int* base;
   {
     std::lock_guard<std::mutex> lk(mu);
     base = pool[dev];
     if (!base) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
       if (cudaMalloc(&base, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
       if (cudaMemset(base, 0, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) {
         cudaFree(base);
