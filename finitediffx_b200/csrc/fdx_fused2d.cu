@@ -17,9 +17,15 @@
 //   Both stencils run at the larger radius P; an axis with a shorter or one-sided stencil has zero taps (the main
 //   region is shrunk so that zero taps still read inside the array).
 // HBM bound: 2s / 3s / 3s bytes per point (laplacian / divergence / gradient), like the 1-D kernels.
+//
+// Big grids (>= 8 MB per field) take the persistent TMA-ring form of the same arithmetic (fused2d_tma_kernel below, the
+// skeleton of fdx_coltma.cu): items = (512-byte strip) x (32 rows) claimed from a global counter, a producer warp fills
+// the ring with halo boxes, four consumer warps walk 8 rows each with a register window along axis 0 and take the
+// axis-1 neighbours from shared memory; the frame by a warp of its own.  Same fma chains: bit-identical results.
 #include <algorithm>
+#include <type_traits>
 
-#include "fdx_common.cuh"
+#include "fdx_tma.cuh"
 
 namespace fdx {
 namespace {
@@ -48,27 +54,79 @@ struct Params2 {
   int64_t frame_points;  // (r0 + n0 - r1) * n1 + (r1 - r0) * (v0 + n1v - v1) * V
 };
 
+// (explicitly rounded product / sum: the frame code is inlined into two kernels and must give the same bits in both --
+// left to the compiler, `acc * alpha + other` may or may not be contracted into an fma)
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
 // one term at one point, from the band or the main stencil of its axis (the frame path)
 template <typename T>
 __device__ __forceinline__ T axis_dot(const Axis2<T>& a, const T* x, int64_t base, int64_t stride, int i) {
+  // taps in ascending order; the loads of four taps are issued together (a frame point is a chain of cold loads
+  // otherwise: ~1 us per tap).  A band tap whose coefficient is exactly zero is skipped (0 * inf must not become NaN).
   T acc = 0;
-  if (i < a.b.nl) {
-    const double* cf = a.b.l + (int64_t)i * a.b.wl;
-    for (int c = 0; c < a.b.wl; ++c) {
-      const T k = (T)__ldg(cf + c);
-      if (k != (T)0) acc = fma(k, __ldg(x + base + (int64_t)c * stride), acc);
-    }
-  } else if (i >= a.n - a.b.nr) {
-    const double* cf = a.b.r + (int64_t)(i - (a.n - a.b.nr)) * a.b.wr;
-    const int64_t c0 = a.n - a.b.wr;
-    for (int c = 0; c < a.b.wr; ++c) {
-      const T k = (T)__ldg(cf + c);
-      if (k != (T)0) acc = fma(k, __ldg(x + base + (c0 + c) * stride), acc);
+  const bool left = i < a.b.nl, right = i >= a.n - a.b.nr;
+  if (left || right) {
+    const int w = left ? a.b.wl : a.b.wr;
+    const double* cf = left ? a.b.l + (int64_t)i * a.b.wl : a.b.r + (int64_t)(i - (a.n - a.b.nr)) * a.b.wr;
+    const T* xp = x + base + (left ? (int64_t)0 : (int64_t)(a.n - a.b.wr) * stride);
+    for (int c = 0; c < w; c += 4) {
+      T k[4], v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int cu = min(c + u, w - 1);
+        k[u] = c + u < w ? (T)__ldg(cf + cu) : (T)0;
+        v[u] = __ldg(xp + (int64_t)cu * stride);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc = k[u] != (T)0 ? fma(k[u], v[u], acc) : acc;
     }
   } else {
-    for (int k = 0; k <= a.hi - a.lo; ++k) acc = fma(a.m[k], __ldg(x + base + (int64_t)(i + a.lo + k) * stride), acc);
+    const int w = a.hi - a.lo + 1;
+    const T* xp = x + base + (int64_t)(i + a.lo) * stride;
+    for (int c = 0; c < w; c += 4) {
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(xp + (int64_t)min(c + u, w - 1) * stride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c + u < w) acc = fma(a.m[c + u], v[u], acc);
+    }
   }
-  return acc * a.alpha;
+  return mul_rn(acc, a.alpha);
+}
+
+// one frame point g (boundary rows with all their columns first, then the boundary vectors of the main rows): each term
+// from its band or its main stencil as the point requires
+template <Op2 OP, typename T, int V>
+__device__ __forceinline__ void frame_point(const Params2<T>& prm, int64_t g) {
+  const int n1 = prm.n1v * V;
+  const int top = prm.r0, bot = prm.ax[0].n - prm.r1;
+  int i0, i1;
+  if (g < (int64_t)(top + bot) * n1) {
+    const int r = (int)(g / n1);
+    i1 = (int)(g - (int64_t)r * n1);
+    i0 = r < top ? r : prm.r1 + (r - top);
+  } else {
+    const int64_t h = g - (int64_t)(top + bot) * n1;
+    const int wl = prm.v0 * V, wr = (prm.n1v - prm.v1) * V;
+    const int r = (int)(h / (wl + wr));
+    const int c = (int)(h - (int64_t)r * (wl + wr));
+    i0 = prm.r0 + r;
+    i1 = c < wl ? c : prm.v1 * V + (c - wl);
+  }
+  const int64_t at = (int64_t)i0 * n1 + i1;
+  const int ci0 = 0, ci1 = OP == DIV2 ? 1 : 0;
+  const T d0 = axis_dot<T>(prm.ax[0], prm.in[ci0], i1, n1, i0);               // along axis 0: column i1
+  const T d1 = axis_dot<T>(prm.ax[1], prm.in[ci1], (int64_t)i0 * n1, 1, i1);  // along axis 1: row i0
+  if constexpr (OP == GRAD2) {
+    prm.out[0][at] = d0;
+    prm.out[1][at] = d1;
+  } else {
+    prm.out[0][at] = add_rn(d0, d1);
+  }
 }
 
 template <Op2 OP, typename T, int V, int P>
@@ -80,31 +138,7 @@ __global__ void __launch_bounds__(128) fused2d_kernel(const __grid_constant__ Pa
   if ((int)blockIdx.x < prm.frame_blocks) {
     // ---- frame: boundary rows (all columns), then the boundary vectors of the main rows
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= prm.frame_points) return;
-    const int top = prm.r0, bot = prm.ax[0].n - prm.r1;
-    int i0, i1;
-    if (g < (int64_t)(top + bot) * n1) {
-      const int r = (int)(g / n1);
-      i1 = (int)(g - (int64_t)r * n1);
-      i0 = r < top ? r : prm.r1 + (r - top);
-    } else {
-      const int64_t h = g - (int64_t)(top + bot) * n1;
-      const int wl = prm.v0 * V, wr = (prm.n1v - prm.v1) * V;
-      const int r = (int)(h / (wl + wr));
-      const int c = (int)(h - (int64_t)r * (wl + wr));
-      i0 = prm.r0 + r;
-      i1 = c < wl ? c : prm.v1 * V + (c - wl);
-    }
-    const int64_t at = (int64_t)i0 * n1 + i1;
-    const int ci0 = OP == DIV2 ? 0 : 0, ci1 = OP == DIV2 ? 1 : 0;
-    const T d0 = axis_dot<T>(prm.ax[0], prm.in[ci0], i1, n1, i0);               // along axis 0: column i1
-    const T d1 = axis_dot<T>(prm.ax[1], prm.in[ci1], (int64_t)i0 * n1, 1, i1);  // along axis 1: row i0
-    if constexpr (OP == GRAD2) {
-      prm.out[0][at] = d0;
-      prm.out[1][at] = d1;
-    } else {
-      prm.out[0][at] = d0 + d1;
-    }
+    if (g < prm.frame_points) frame_point<OP, T, V>(prm, g);
     return;
   }
   // ---- main region
@@ -182,6 +216,255 @@ __global__ void __launch_bounds__(128) fused2d_kernel(const __grid_constant__ Pa
   }
 }
 
+// ------------------------------------------------------------------------------ persistent TMA-ring form (big grids)
+template <Op2 OP, typename T, int P>
+struct Geo2 {
+  static constexpr int V = 16 / (int)sizeof(T), W = 2 * P + 1, HXV = (P + V - 1) / V;
+  static constexpr int TXV = 32, TX = TXV * V;
+  static constexpr int NW = 4, RW = 8, RB = NW * RW, NFW = 2, NT = (NW + 1 + NFW) * 32;  // consumers, producer, frame warps
+  // field a (axis-0 stencil): RB + 2P rows; with the x halos when it is also the field of the axis-1 stencil
+  static constexpr int AX = OP == DIV2 ? TX : TX + 2 * HXV * V, AY = RB + 2 * P;
+  static constexpr int A_BYTES = ((AX * AY * (int)sizeof(T) + 127) / 128) * 128;
+  // field b (DIV2 only: the axis-1 stencil's field): RB rows with x halos
+  static constexpr int BX = TX + 2 * HXV * V, BY = RB;
+  static constexpr int B_BYTES = OP == DIV2 ? ((BX * BY * (int)sizeof(T) + 127) / 128) * 128 : 0;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = OP == DIV2 ? 3 : 4, CLAIM = 4;
+  static constexpr int SMEM_BYTES = 256 + 128 + STAGES * STAGE_BYTES;
+};
+
+template <typename T>
+struct TmaExtra {
+  CUtensorMap tmap[2];
+  int strips, rblocks;
+  unsigned int items;
+  unsigned int* ctr;
+};
+
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for2(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for2<I + 1, N>(f);
+  }
+}
+
+template <Op2 OP, typename T, int P>
+__global__ void __launch_bounds__(224, 2) fused2d_tma_kernel(const __grid_constant__ Params2<T> prm, const __grid_constant__ TmaExtra<T> ex) {
+  using namespace tma;
+  using G = Geo2<OP, T, P>;
+  constexpr int V = G::V, W = G::W, HXV = G::HXV, STAGES = G::STAGES, RW = G::RW;
+  using VT = Vec<T, V>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t ring = (smem0 + 256u + 127u) & ~127u;
+  const uint32_t bar_full = smem0, bar_empty = smem0 + 8u * STAGES, item_xy = smem0 + 128u;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int b = blockIdx.x, gsz = gridDim.x;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8u * s, 1);
+      mbar_init(bar_empty + 8u * s, G::NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&ex.tmap[0]) : "memory");
+    if constexpr (OP == DIV2) asm volatile("prefetch.tensormap [%0];" ::"l"(&ex.tmap[1]) : "memory");
+  }
+  __syncthreads();
+
+  // ---- producer warp
+  if (wrp == G::NW) {
+    if (lane != 0) return;
+    unsigned int base = 0;
+    int left = 0;
+    for (int k = 0;; ++k) {
+      if (left == 0) base = atomicAdd(ex.ctr, (unsigned)G::CLAIM), left = G::CLAIM;
+      const unsigned int t = base++;
+      --left;
+      const int s = k % STAGES;
+      if (k >= STAGES) mbar_wait(bar_empty + 8u * s, (uint32_t)((k / STAGES) - 1) & 1u);
+      if (t < ex.items) {
+        const int rb = (int)(t / (unsigned)ex.strips), strip = (int)(t - (unsigned)rb * (unsigned)ex.strips);
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(item_xy + 8u * s), "r"(strip), "r"(rb) : "memory");
+        const int x0 = (prm.v0 + strip * G::TXV) * V, y0 = prm.r0 + rb * G::RB;
+        const uint32_t dst = ring + (uint32_t)s * G::STAGE_BYTES;
+        if constexpr (OP == DIV2) {
+          mbar_expect_tx(bar_full + 8u * s, (uint32_t)((G::AX * G::AY + G::BX * G::BY) * sizeof(T)));
+          tma_load_2d(dst, &ex.tmap[0], bar_full + 8u * s, x0, y0 - P);
+          tma_load_2d(dst + G::A_BYTES, &ex.tmap[1], bar_full + 8u * s, x0 - HXV * V, y0);
+        } else {
+          mbar_expect_tx(bar_full + 8u * s, (uint32_t)(G::AX * G::AY * sizeof(T)));
+          tma_load_2d(dst, &ex.tmap[0], bar_full + 8u * s, x0 - HXV * V, y0 - P);
+        }
+      } else {
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(item_xy + 8u * s), "r"(-1), "r"(-1) : "memory");
+        mbar_arrive(bar_full + 8u * s);
+        break;
+      }
+    }
+    __threadfence();
+    if (atomicAdd(ex.ctr + 1, 1u) == (unsigned)gsz - 1u) {  // the last producer of the grid rewinds the counters
+      ex.ctr[0] = 0u, ex.ctr[1] = 0u;
+      __threadfence();
+    }
+    return;
+  }
+  // ---- frame warps
+  if (wrp > G::NW) {
+    const int fl = (wrp - G::NW - 1) * 32 + lane;
+    for (int64_t g = (int64_t)b * (G::NFW * 32) + fl; g < prm.frame_points; g += (int64_t)gsz * (G::NFW * 32)) frame_point<OP, T, V>(prm, g);
+    return;
+  }
+  // ---- consumer warps
+  const Axis2<T>& A0 = prm.ax[0];
+  const Axis2<T>& A1 = prm.ax[1];
+  const int n1 = prm.n1v * V;
+  constexpr int APITCH = G::AX * (int)sizeof(T), BPITCH = G::BX * (int)sizeof(T);
+  constexpr int AXOFF = OP == DIV2 ? 0 : HXV * 16;  // byte offset of this lane's own vector inside a row of field a
+  int stage = 0;
+  uint32_t parity = 0;
+  for (;;) {
+    mbar_wait(bar_full + 8u * stage, parity);
+    int strip, rb;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(strip), "=r"(rb) : "r"(item_xy + 8u * stage));
+    if (strip < 0) break;
+    const int jv = prm.v0 + strip * G::TXV + lane;
+    const int i0 = prm.r0 + rb * G::RB + wrp * RW;
+    const uint32_t sa = ring + (uint32_t)stage * G::STAGE_BYTES + (uint32_t)(wrp * RW * APITCH + AXOFF + lane * 16);  // box row of input row i0 - P
+    const uint32_t sb = OP == DIV2 ? ring + (uint32_t)stage * G::STAGE_BYTES + (uint32_t)(G::A_BYTES + wrp * RW * BPITCH + lane * 16)
+                                   : sa + (uint32_t)(P * APITCH) - (uint32_t)(HXV * 16);  // first window vector of output row i0
+    const bool col_ok = jv < prm.v1;
+    const int64_t at0 = (int64_t)i0 * n1 + (int64_t)jv * V;
+    VT q[W];
+    static_for2<0, W - 1>([&](auto s_) { q[s_.value] = lds_vec<T, V>(sa + (uint32_t)(s_.value * APITCH)); });
+    static_for2<0, RW>([&](auto r_) {
+      constexpr int r = r_.value;
+      q[(W - 1 + r) % W] = lds_vec<T, V>(sa + (uint32_t)((W - 1 + r) * APITCH));
+      // axis 0: taps over the window (slot (r + k) % W holds input row i0 + r - P + k)
+      VT d0;
+      if constexpr (sizeof(T) == 4) {  // packed pairs (FFMA2: two independent fmas, the bits of the scalar chain)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          unsigned long long a;
+          asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(pack2(A0.c[0], A0.c[0])), "l"(pack2(q[r % W].v[2 * h], q[r % W].v[2 * h + 1])));
+          static_for2<1, W>([&](auto k_) {
+            constexpr int k = k_.value;
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(pack2(A0.c[k], A0.c[k])), "l"(pack2(q[(r + k) % W].v[2 * h], q[(r + k) % W].v[2 * h + 1])));
+          });
+          unpack2(a, d0.v[2 * h], d0.v[2 * h + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          T acc = A0.c[0] * q[r % W].v[v];
+          static_for2<1, W>([&](auto k_) { acc = fma(A0.c[k_.value], q[(r + k_.value) % W].v[v], acc); });
+          d0.v[v] = acc;
+        }
+      }
+      // axis 1: this row's vector and its neighbours from shared memory
+      T w[(2 * HXV + 1) * V];
+#pragma unroll
+      for (int u = 0; u < 2 * HXV + 1; ++u) {
+        VT t;
+        if (OP != DIV2 && u == HXV)
+          t = q[(r + P) % W];  // the centre vector is already in the window
+        else
+          t = lds_vec<T, V>(sb + (uint32_t)(r * (OP == DIV2 ? BPITCH : APITCH) + u * 16));
+#pragma unroll
+        for (int v = 0; v < V; ++v) w[u * V + v] = t.v[v];
+      }
+      VT d1;
+      if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float s0 = A1.c[0] * w[HXV * V + 2 * h - P], s1 = A1.c[0] * w[HXV * V + 2 * h + 1 - P];
+#pragma unroll
+          for (int k = 1; k < W; ++k) {
+            const int j = HXV * V + 2 * h - P + k;
+            if (j % 2 == 0) {
+              unsigned long long a = pack2(s0, s1);
+              asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(pack2(A1.c[k], A1.c[k])), "l"(pack2(w[j], w[j + 1])));
+              unpack2(a, s0, s1);
+            } else {
+              s0 = fma(A1.c[k], w[j], s0), s1 = fma(A1.c[k], w[j + 1], s1);
+            }
+          }
+          d1.v[2 * h] = s0, d1.v[2 * h + 1] = s1;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          T acc = A1.c[0] * w[HXV * V + v - P];
+#pragma unroll
+          for (int k = 1; k < W; ++k) acc = fma(A1.c[k], w[HXV * V + v - P + k], acc);
+          d1.v[v] = acc;
+        }
+      }
+      if (col_ok && i0 + r < prm.r1) {
+        const int64_t at = at0 + (int64_t)r * n1;
+        if constexpr (OP == GRAD2) {
+          st_vec<T, V>(prm.out[0] + at, d0);
+          st_vec<T, V>(prm.out[1] + at, d1);
+        } else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) d0.v[v] += d1.v[v];
+          st_vec<T, V>(prm.out[0] + at, d0);
+        }
+      }
+    });
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8u * stage);
+    if (++stage == STAGES) stage = 0, parity ^= 1u;
+  }
+}
+
+template <Op2 OP, typename T, int P>
+static int launch2_tma(Params2<T>& prm, cudaStream_t st) {
+  using namespace tma;
+  using G = Geo2<OP, T, P>;
+  const int rows = prm.r1 - prm.r0, vecs = prm.v1 - prm.v0;
+  const int n0 = prm.ax[0].n, n1 = prm.n1v * G::V;
+  if (rows <= 0 || vecs <= 0) return FDX_EUNSUPPORTED;
+  if ((int64_t)n0 * n1 * (int64_t)sizeof(T) < (int64_t)env_int("FDX_FUSED2D_TMA_MIN_MB", 8) * (1 << 20) || env_int("FDX_FUSED2D_TMA_DISABLE", 0)) return FDX_EUNSUPPORTED;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return FDX_EUNSUPPORTED;
+  TmaExtra<T> ex;
+  auto make = [&](CUtensorMap* m, const T* base, int bx, int by) {
+    cuuint64_t dims[2] = {(cuuint64_t)n1, (cuuint64_t)n0};
+    cuuint64_t strides[1] = {(cuuint64_t)n1 * sizeof(T)};
+    cuuint32_t box[2] = {(cuuint32_t)bx, (cuuint32_t)by};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!make(&ex.tmap[0], prm.in[0], G::AX, G::AY)) return FDX_EUNSUPPORTED;
+  if (OP == DIV2 && !make(&ex.tmap[1], prm.in[1], G::BX, G::BY)) return FDX_EUNSUPPORTED;
+  const int64_t strips = (vecs + G::TXV - 1) / G::TXV, rblocks = (rows + G::RB - 1) / G::RB;
+  if (strips * rblocks > 0x3fffffffLL) return FDX_EUNSUPPORTED;
+  ex.strips = (int)strips, ex.rblocks = (int)rblocks, ex.items = (unsigned)(strips * rblocks);
+  ex.ctr = claim_slot(st);
+  if (!ex.ctr) return FDX_EUNSUPPORTED;
+  auto kern = fused2d_tma_kernel<OP, T, P>;
+  {
+    static std::atomic<unsigned long long> attr_done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (!bit || !(attr_done.load(std::memory_order_acquire) & bit)) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      attr_done.fetch_or(bit, std::memory_order_release);
+    }
+  }
+  const int per_sm = std::max(1, std::min(4, (int)(224 * 1024 / (G::SMEM_BYTES + 1024))));
+  const int64_t grid = std::min<int64_t>(ex.items, (int64_t)num_sms() * per_sm);
+  kern<<<(unsigned)grid, G::NT, G::SMEM_BYTES, st>>>(prm, ex);
+  count_launch(OP == LAP2 ? "fused_laplacian2d_tma" : OP == DIV2 ? "fused_divergence2d_tma" : "fused_gradient2d_tma");
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
 template <Op2 OP, typename T, int P>
 int launch2(const fdx_plan_s* const plans[2], const T* const in[2], T* const out[2], const double alpha[2], cudaStream_t st) {
   constexpr int V = 16 / (int)sizeof(T);
@@ -208,6 +491,11 @@ int launch2(const fdx_plan_s* const plans[2], const T* const in[2], T* const out
   if (prm.v1 < prm.v0) prm.v1 = prm.v0;
   const int rows = prm.r1 - prm.r0, vecs = prm.v1 - prm.v0;
   prm.frame_points = (int64_t)(n0 - rows) * n1 + (int64_t)rows * (prm.n1v - vecs) * V;
+  prm.frame_blocks = 0;
+  {
+    const int rc = launch2_tma<OP, T, P>(prm, st);  // big grids: the persistent TMA-ring form
+    if (rc != FDX_EUNSUPPORTED) return rc;
+  }
   const int64_t fb = (prm.frame_points + 127) / 128;
   prm.n_tiles = std::max(1, (vecs + 127) / 128);
   // rows per chunk as in axis_stream: long chunks for long stencils (W - 1 halo rows are re-read per chunk), but

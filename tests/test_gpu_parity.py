@@ -619,7 +619,7 @@ def test_fused_2d_operators(dtype, method):
                 continue
             xt = _gpu(arr).requires_grad_(True)
             out = getattr(fdx, op)(xt, **kw)
-            assert _cabi.last_kernel().startswith("fused_") and _cabi.last_kernel().endswith("2d"), (op, shape, kw, _cabi.last_kernel())
+            assert _cabi.last_kernel().startswith("fused_") and _cabi.last_kernel().endswith(("2d", "2d_tma")), (op, shape, kw, _cabi.last_kernel())
             ref = getattr(O, op)(arr, **kw)
             assert out.shape == ref.shape
             err = parity_error(op, arr, kw, out.detach().cpu().numpy(), ref)
@@ -627,7 +627,7 @@ def test_fused_2d_operators(dtype, method):
             # vjp == oracle: flatten the operator through dense per-axis matrices
             g = rng.standard_normal(ref.shape).astype(dtype)
             (gx,) = torch.autograd.grad(out, xt, _gpu(g))
-            assert _cabi.last_kernel().endswith("2d"), (op, shape, kw, "vjp", _cabi.last_kernel())
+            assert _cabi.last_kernel().endswith(("2d", "2d_tma")), (op, shape, kw, "vjp", _cabi.last_kernel())
             hs = kw["step_size"] if isinstance(kw["step_size"], tuple) else (kw["step_size"],) * 2
             accs = acc if isinstance(acc, tuple) else (acc,) * 2
             D = [O.dense_matrix(shape[k], accuracy=accs[k], derivative=d, method=method, step_size=hs[k]) for k in range(2)]
@@ -658,10 +658,14 @@ def test_fused_2d_large_and_fallbacks():
     x = torch.randn((2048, 2048), device="cuda", generator=gen)
     kw = dict(accuracy=4, step_size=(0.1, 0.2))
     out = fdx.laplacian(x, **kw)
-    assert _cabi.last_kernel() == "fused_laplacian2d"
+    assert _cabi.last_kernel() == "fused_laplacian2d_tma"  # 16 MB: the persistent TMA-ring form
+    with _env(FDX_FUSED2D_TMA_DISABLE=1):
+        plain = fdx.laplacian(x, **kw)
+        assert _cabi.last_kernel() == "fused_laplacian2d"
+    assert torch.equal(out, plain)
     with _env(FDX_FUSED2D_DISABLE=1):
         ref = fdx.laplacian(x, **kw)
-        assert _cabi.last_kernel() != "fused_laplacian2d"
+        assert not _cabi.last_kernel().startswith("fused_laplacian2d")
     assert ((out - ref).abs().max() / ref.abs().max()).item() < 2e-6
     cols = x[:, :64].cpu().numpy()  # full columns: the oracle's artificial edge is the right one, 24 columns away from the compared ones
     oc = O.laplacian(cols, **kw)
@@ -721,3 +725,42 @@ def test_col_tma_kernel_equals_axis_stream_bit_for_bit_and_the_oracle(dtype):
             assert np.array_equal(out, other), (shape, axis, method, d, a, float(np.abs(out - other).max()))
             err = parity_error("difference", x, kw, out, O.difference(x, **kw))
             assert err <= TOL[np.dtype(dtype)], (shape, axis, method, d, a, err)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_fused_2d_tma_form_equals_the_plain_form_bit_for_bit(dtype):
+    """Big 2-D grids take the persistent TMA-ring form of the fused 2-D kernels.  Forced onto small awkward shapes
+    (partial last strip / row block, main regions smaller than one item) it must equal the plain form bit for bit --
+    forward and vjp (transposed plans: wide frames), all operators and methods; the plain form is the one checked
+    against the oracle in test_fused_2d_operators."""
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    v = 4 if dtype == torch.float32 else 2
+    for shape in ((70, 33 * v), (45, 32 * v), (130, 70 * v), (20, 40 * v)):
+        x = torch.randn(shape, device="cuda", dtype=dtype, generator=gen)
+        f = torch.randn((2,) + shape, device="cuda", dtype=dtype, generator=gen)
+        for method in O.METHODS:
+            for op, arr, kw in (("laplacian", x, dict(accuracy=4, step_size=(0.1, 0.3))), ("laplacian", x, dict(accuracy=(2, 5), step_size=0.5)),
+                                ("gradient", x, dict(accuracy=3, step_size=(0.1, 0.3))), ("divergence", f, dict(accuracy=2, step_size=(0.1, 0.3), keepdims=False)),
+                                ("curl", f, dict(accuracy=4, step_size=(0.1, 0.3)))):
+                kw = dict(kw, method=method)
+                acc = kw["accuracy"]
+                amax = max(acc) if isinstance(acc, tuple) else acc
+                d = 2 if op == "laplacian" else 1
+                if (method != "central" and d + amax - 1 > 6) or min(shape) < 2 * (d + amax):
+                    continue
+
+                def run():
+                    a = arr.clone().requires_grad_(True)
+                    out = getattr(fdx, op)(a, **kw)
+                    k1 = _cabi.last_kernel()
+                    g = torch.ones_like(out) * 0.5 + out.detach() * 0.25
+                    (ga,) = torch.autograd.grad(out, a, g)
+                    return out.detach(), ga, k1
+
+                with _env(FDX_FUSED2D_TMA_MIN_MB=0):
+                    o1, g1, k1 = run()
+                with _env(FDX_FUSED2D_TMA_DISABLE=1):
+                    o2, g2, k2 = run()
+                assert k1.endswith("2d_tma") and k2.endswith("2d"), (op, shape, kw, k1, k2)
+                assert torch.equal(o1, o2), (op, shape, kw, (o1 - o2).abs().max().item())
+                assert torch.equal(g1, g2), (op, shape, kw, "vjp", (g1 - g2).abs().max().item())
