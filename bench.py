@@ -609,7 +609,24 @@ def _extras_single(fdx, _cabi, dev, peak):
             "worst": _entry(pts, 8, worst[0], peak, case=list(worst[1:])),
             "note": "per call through the public API (host launch path included); per case the better of two runs of 10 calls",
         }
-    del x
+    # ---- beyond the BASELINE configs: the 2-D operators on the same 8192^2 grid (most of the reference's own tests are 2-D)
+    f2 = torch.randn((2, 8192, 8192), device=dev)
+    for name, call, arr, fields in (("laplacian2d_8192sq_f32_a4", lambda v: fdx.laplacian(v, accuracy=4, step_size=0.1), x, 2),
+                                    ("gradient2d_8192sq_f32_a4", lambda v: fdx.gradient(v, accuracy=4, step_size=0.1), x, 3),
+                                    ("divergence2d_8192sq_f32_a4", lambda v: fdx.divergence(v, accuracy=4, step_size=0.1), f2, 3),
+                                    ("curl2d_8192sq_f32_a4", lambda v: fdx.curl(v, accuracy=4, step_size=0.1), f2, 3)):
+        t = timed(call, [arr], k=10, wu=3)
+        ex[name] = _entry(pts, 4 * fields, t, peak, _cabi.last_kernel())
+    del x, f2
+    torch.cuda.empty_cache()
+    # ---- jacobian and hessian on 3-D grids (algorithmic bytes: one read per input field, one write per output field)
+    f3 = torch.randn((3, 384, 384, 384), device=dev)
+    t = timed(lambda v: fdx.jacobian(v, accuracy=4, step_size=0.1), [f3], k=10, wu=3)
+    ex["jacobian_3x384_f32_a4"] = _entry(384**3, 4 * (3 + 9), t, peak, _cabi.last_kernel(), note="one fused gradient per component")
+    t = timed(lambda v: fdx.hessian(v, accuracy=4, step_size=0.1), [f3[0]], k=10, wu=3)
+    ex["hessian_384_f32_a4"] = _entry(384**3, 4 * (1 + 9), t, peak, _cabi.last_kernel(),
+                                      note="7 axis passes + 4 slot copies (the reference's table entries, bug-compatible); frac counts one read + nine writes")
+    del f3
     torch.cuda.empty_cache()
     # ---- config 4: divergence / curl on a (3, 1024^3) fp32 field, accuracy 4 (one input: 12.9 GB, far larger than L2)
     for name in ("divergence_1024_f32_a4_strong", "curl_1024_f32_a4_strong"):

@@ -93,6 +93,8 @@ EXPORTS = (
     "fdx_divergence2d_f64",
     "fdx_gradient2d_f32",
     "fdx_gradient2d_f64",
+    "fdx_axis_apply_dup_f32",
+    "fdx_axis_apply_dup_f64",
 )
 
 
@@ -115,14 +117,21 @@ def load():
             )
         lib = C.CDLL(_LIB_PATH)
         if os.environ.get("FDX_B200_LIB"):  # A/B timing against an older build: newer entry points may be missing
+            def _missing(name):
+                def stub(*a, **k):
+                    raise FdxError(f"{name} is not exported by {_LIB_PATH} (an older build selected with FDX_B200_LIB)")
+
+                return stub
+
             for name in EXPORTS:
                 if not hasattr(lib, name):
-                    setattr(lib, name, lambda *a, **k: 0)
+                    setattr(lib, name, _missing(name))
         vp, i64, dbl, i32 = C.c_void_p, C.c_int64, C.c_double, C.c_int
         lib.fdx_plan_create.argtypes = [C.POINTER(vp), C.POINTER(_AxisDesc)]
         lib.fdx_plan_destroy.argtypes = [vp]
         for sfx in ("f32", "f64"):
             getattr(lib, f"fdx_axis_apply_{sfx}").argtypes = [vp, vp, vp, i64, i64, dbl, i32, vp]
+            getattr(lib, f"fdx_axis_apply_dup_{sfx}").argtypes = [vp, vp, vp, vp, vp, i64, i64, dbl, vp]
             getattr(lib, f"fdx_laplacian2d_{sfx}").argtypes = [C.POINTER(vp), vp, vp, C.POINTER(dbl), vp]
             getattr(lib, f"fdx_divergence2d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(dbl), vp]
             getattr(lib, f"fdx_gradient2d_{sfx}").argtypes = [C.POINTER(vp), vp, C.POINTER(vp), C.POINTER(dbl), vp]
@@ -264,6 +273,28 @@ def axis_apply(plan: AxisPlan, x: torch.Tensor, out: torch.Tensor, axis: int, al
             fn(dp.handle, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), outer, inner, float(alpha), int(bool(accumulate)), _stream_ptr(x.device)),
             "fdx_axis_apply",
         )
+
+
+def axis_apply_dup(plan: AxisPlan, x: torch.Tensor, outs: Sequence[torch.Tensor], axis: int, alpha: float):
+    """outs[0] = outs[1] (= outs[2]) = alpha * D_axis x: one pass that stores its result in up to three arrays (the
+    hessian's repeated table entries, reference finite_diff.py:524-529)."""
+    outs = list(outs)
+    assert 1 <= len(outs) <= 3
+    _require(x, "x")
+    for o in outs:
+        _require(o, "out")
+        assert x.shape == o.shape and x.dtype == o.dtype
+    if x.numel() == 0:
+        return
+    shape = x.shape
+    assert shape[axis] == plan.n, (shape, axis, plan.n)
+    outer = int(np.prod(shape[:axis], dtype=np.int64)) if axis > 0 else 1
+    inner = int(np.prod(shape[axis + 1 :], dtype=np.int64)) if axis + 1 < len(shape) else 1
+    dp = device_plan(plan, x.device)
+    ptr = [C.c_void_p(o.data_ptr()) for o in outs] + [C.c_void_p(0)] * (3 - len(outs))
+    with _on_device(x.device):
+        fn = getattr(load(), f"fdx_axis_apply_dup_{_sfx(x)}")
+        check(fn(dp.handle, C.c_void_p(x.data_ptr()), ptr[0], ptr[1], ptr[2], outer, inner, float(alpha), _stream_ptr(x.device)), "fdx_axis_apply_dup")
 
 
 def axis_apply_dev_alpha(plan: AxisPlan, x: torch.Tensor, out: torch.Tensor, axis: int, alpha_dev: torch.Tensor, sign: float = 1.0,

@@ -25,9 +25,10 @@ namespace fdx {
 
 // fdx_rowtma.cu / fdx_coltma.cu: the contiguous axis / a strided axis of big aligned arrays (FDX_EUNSUPPORTED: not their case)
 template <typename T>
-int col_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, cudaStream_t st, bool* band_done);
+int col_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, cudaStream_t st, bool* band_done, T* out2 = nullptr,
+                  T* out3 = nullptr);
 template <typename T>
-int row_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done);
+int row_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done, T* out2 = nullptr, T* out3 = nullptr);
 
 // ---------------------------------------------------------------------------------- band rows
 // The few boundary rows with their own dense taps.  One element per thread; `g` numbers the band elements of the
@@ -419,7 +420,41 @@ static int apply_checked(fdx_plan_t plan, const T* x, T* out, int64_t outer, int
                     : apply_impl<T, false>(plan, x, out, outer, inner, alpha, st, alpha_dev);
 }
 
+// out = out2 = out3 = alpha * D x in one pass where the TMA kernels take the call (their stores are simply repeated);
+// otherwise the ordinary pass into `out` and device-to-device copies behind it on the same stream.
+template <typename T>
+static int apply_dup(fdx_plan_t plan, const T* x, T* out, T* out2, T* out3, int64_t outer, int64_t inner, double alpha, void* stream) {
+  if (!out2 && out3) out2 = out3, out3 = nullptr;
+  if (!out2) return apply_checked<T>(plan, x, out, outer, inner, alpha, 0, stream);
+  if (!plan || !x || !out || outer < 0 || inner < 0) return FDX_EINVAL;
+  if ((((uintptr_t)x | (uintptr_t)out | (uintptr_t)out2 | (uintptr_t)out3) & (sizeof(T) - 1)) != 0) return FDX_EALIGN;
+  if (outer == 0 || inner == 0 || plan->n == 0) return FDX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool band_done = false;
+  int rc = FDX_EUNSUPPORTED;
+  if (plan->n - plan->nl - plan->nr > 0)
+    rc = inner > 1 ? col_tma_apply<T>(plan, x, out, outer, inner, alpha, st, &band_done, out2, out3)
+                   : row_tma_apply<T>(plan, x, out, outer, alpha, st, &band_done, out2, out3);
+  if (rc != FDX_EUNSUPPORTED) return rc;
+  rc = apply_checked<T>(plan, x, out, outer, inner, alpha, 0, stream);
+  if (rc != FDX_OK) return rc;
+  const size_t bytes = (size_t)outer * (size_t)plan->n * (size_t)inner * sizeof(T);
+  FDX_CUDA_TRY(cudaMemcpyAsync(out2, out, bytes, cudaMemcpyDeviceToDevice, st));
+  if (out3) FDX_CUDA_TRY(cudaMemcpyAsync(out3, out, bytes, cudaMemcpyDeviceToDevice, st));
+  return FDX_OK;
+}
+
 }  // namespace fdx
+
+extern "C" int fdx_axis_apply_dup_f32(fdx_plan_t plan, const float* x, float* out, float* out2, float* out3, int64_t outer, int64_t inner,
+                                      double alpha, void* stream) {
+  return fdx::apply_dup<float>(plan, x, out, out2, out3, outer, inner, alpha, stream);
+}
+
+extern "C" int fdx_axis_apply_dup_f64(fdx_plan_t plan, const double* x, double* out, double* out2, double* out3, int64_t outer, int64_t inner,
+                                      double alpha, void* stream) {
+  return fdx::apply_dup<double>(plan, x, out, out2, out3, outer, inner, alpha, stream);
+}
 
 extern "C" int fdx_axis_apply_f32(fdx_plan_t plan, const float* x, float* out, int64_t outer, int64_t inner, double alpha,
                                   int accumulate, void* stream) {

@@ -39,6 +39,7 @@ struct Params {
   CUtensorMap tmap;  // (inner, n, outer)
   const T* x;
   T* out;
+  T *out2, *out3;  // optional further destinations of the same values (nullptr: none)
   int64_t inner;
   int n, inner_v, outer, r0, r1, lo;
   int strips, rblocks;  // ceil(inner / TX), ceil((r1 - r0) / RB)
@@ -143,7 +144,11 @@ __global__ void __launch_bounds__(192, 2) axis_coltma_kernel(const __grid_consta
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc = cf[u] != (T)0 ? fma(cf[u], xv[u], acc) : acc;
       }
-      prm.out[(o * prm.n + row) * prm.inner + j] = acc * prm.alpha;
+      const T val = acc * prm.alpha;
+      const int64_t at = (o * prm.n + row) * prm.inner + j;
+      prm.out[at] = val;
+      if (prm.out2) prm.out2[at] = val;
+      if (prm.out3) prm.out3[at] = val;
     }
     return;
   }
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(192, 2) axis_coltma_kernel(const __grid_consta
     const int jv = strip * G::TXV + lane;         // this lane's vector column
     const int i0 = prm.r0 + rb * G::RB + wrp * RW;  // first output row of this warp
     const uint32_t base = ring + (uint32_t)stage * G::STAGE_BYTES + (uint32_t)(wrp * RW * G::ROW_BYTES + lane * 16);
-    T* op = prm.out + ((int64_t)o * prm.n + i0) * prm.inner + (int64_t)jv * V;
+    const int64_t at0 = ((int64_t)o * prm.n + i0) * prm.inner + (int64_t)jv * V;
     const bool col_ok = jv < prm.inner_v;
     VT q[W];
     static_for<0, W - 1>([&](auto s) { q[s.value] = lds_vec<T, V>(base + (uint32_t)(s.value * G::ROW_BYTES)); });
@@ -188,7 +193,12 @@ __global__ void __launch_bounds__(192, 2) axis_coltma_kernel(const __grid_consta
           res.v[v] = acc;
         }
       }
-      if (col_ok && i0 + r < prm.r1) st_vec<T, V>(op + (int64_t)r * prm.inner, res);
+      if (col_ok && i0 + r < prm.r1) {
+        const int64_t at = at0 + (int64_t)r * prm.inner;
+        st_vec<T, V>(prm.out + at, res);
+        if (prm.out2) st_vec<T, V>(prm.out2 + at, res);
+        if (prm.out3) st_vec<T, V>(prm.out3 + at, res);
+      }
     });
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8u * stage);
@@ -197,7 +207,7 @@ __global__ void __launch_bounds__(192, 2) axis_coltma_kernel(const __grid_consta
 }
 
 template <typename T, int W>
-static int launch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, cudaStream_t st, bool* band_done) {
+static int launch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, cudaStream_t st, bool* band_done, T* out2, T* out3) {
   using G = Geo<T, W>;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return FDX_EUNSUPPORTED;
@@ -214,7 +224,7 @@ static int launch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_
   const int64_t strips = (inner + G::TX - 1) / G::TX, rblocks = (r1 - r0 + G::RB - 1) / G::RB;
   const int64_t items = strips * rblocks * outer;
   if (items > 0x3fffffffLL || strips > 0x7fffffffLL / G::TX) return FDX_EUNSUPPORTED;
-  prm.x = x, prm.out = out, prm.inner = inner, prm.n = p->n, prm.inner_v = (int)(inner / G::V), prm.outer = (int)outer;
+  prm.x = x, prm.out = out, prm.out2 = out2, prm.out3 = out3, prm.inner = inner, prm.n = p->n, prm.inner_v = (int)(inner / G::V), prm.outer = (int)outer;
   prm.r0 = r0, prm.r1 = r1, prm.lo = p->lo, prm.strips = (int)strips, prm.rblocks = (int)rblocks, prm.items = (unsigned)items;
   prm.b = bands_of(p), prm.alpha = (T)alpha, prm.taps = scaled_taps<T>(p, alpha);
   prm.band_total = outer * (int64_t)(p->nl + p->nr) * inner;
@@ -242,11 +252,11 @@ static int launch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_
 }
 
 template <typename T>
-static int dispatch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, cudaStream_t st, bool* band_done) {
+static int dispatch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, cudaStream_t st, bool* band_done, T* out2, T* out3) {
   switch (p->hi - p->lo + 1) {
 #define FDX_CASE(W_) \
   case W_:           \
-    return launch<T, W_>(p, x, out, outer, inner, alpha, st, band_done);
+    return launch<T, W_>(p, x, out, outer, inner, alpha, st, band_done, out2, out3);
     FDX_CASE(2) FDX_CASE(3) FDX_CASE(4) FDX_CASE(5) FDX_CASE(6) FDX_CASE(7) FDX_CASE(8) FDX_CASE(9) FDX_CASE(10)
     FDX_CASE(11) FDX_CASE(12) FDX_CASE(13) FDX_CASE(14) FDX_CASE(15) FDX_CASE(16)
 #undef FDX_CASE
@@ -259,16 +269,16 @@ static int dispatch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int6
 
 // Entry for fdx_axis.cu: FDX_EUNSUPPORTED = not this kernel's case (the caller goes on to axis_stream).
 template <typename T>
-int col_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, cudaStream_t st, bool* band_done) {
+int col_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, int64_t inner, double alpha, cudaStream_t st, bool* band_done, T* out2, T* out3) {
   constexpr int V = 16 / (int)sizeof(T);
   if (env_int("FDX_COLTMA_DISABLE", 0)) return FDX_EUNSUPPORTED;
-  if (inner % V != 0 || (((uintptr_t)x | (uintptr_t)out) & 15) != 0) return FDX_EUNSUPPORTED;
+  if (inner % V != 0 || (((uintptr_t)x | (uintptr_t)out | (uintptr_t)out2 | (uintptr_t)out3) & 15) != 0) return FDX_EUNSUPPORTED;
   if (p->n - p->nl - p->nr <= 0 || outer <= 0 || outer > 0x7fffffffLL || inner < 32 * V) return FDX_EUNSUPPORTED;
   const int64_t bytes = outer * (int64_t)p->n * inner * (int64_t)sizeof(T);
   if (bytes < (int64_t)env_int("FDX_COLTMA_MIN_MB", 8) * (1 << 20)) return FDX_EUNSUPPORTED;
-  return coltma::dispatch<T>(p, x, out, outer, inner, alpha, st, band_done);
+  return coltma::dispatch<T>(p, x, out, outer, inner, alpha, st, band_done, out2, out3);
 }
-template int col_tma_apply<float>(const fdx_plan_s*, const float*, float*, int64_t, int64_t, double, cudaStream_t, bool*);
-template int col_tma_apply<double>(const fdx_plan_s*, const double*, double*, int64_t, int64_t, double, cudaStream_t, bool*);
+template int col_tma_apply<float>(const fdx_plan_s*, const float*, float*, int64_t, int64_t, double, cudaStream_t, bool*, float*, float*);
+template int col_tma_apply<double>(const fdx_plan_s*, const double*, double*, int64_t, int64_t, double, cudaStream_t, bool*, double*, double*);
 
 }  // namespace fdx

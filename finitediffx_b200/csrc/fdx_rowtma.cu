@@ -44,6 +44,7 @@ struct Params {
   CUtensorMap tmap;
   const T* x;
   T* out;
+  T *out2, *out3;  // optional further destinations of the same values (nullptr: none)
   int rows;  // outer
   int n, n_v, r0, r1;
   int strips;       // ceil(n / TX)
@@ -139,7 +140,10 @@ __global__ void __launch_bounds__(192, 5) axis_rowtma_kernel(const __grid_consta
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc = cf[u] != (T)0 ? fma(cf[u], xv[u], acc) : acc;
       }
-      prm.out[o * prm.n + row] = acc * prm.alpha;
+      const T val = acc * prm.alpha;
+      prm.out[o * prm.n + row] = val;
+      if (prm.out2) prm.out2[o * prm.n + row] = val;
+      if (prm.out3) prm.out3[o * prm.n + row] = val;
     }
     return;
   }
@@ -200,14 +204,20 @@ __global__ void __launch_bounds__(192, 5) axis_rowtma_kernel(const __grid_consta
         }
       }
       if (has_main && row < prm.rows) {
-        T* orow = prm.out + (int64_t)row * prm.n + i_first;
-        if (whole) {
-          st_vec<T, V>(orow, res);
-        } else {
+        const int64_t at = (int64_t)row * prm.n + i_first;
+        auto put = [&](T* dst) {
+          T* orow = dst + at;
+          if (whole) {
+            st_vec<T, V>(orow, res);
+          } else {
 #pragma unroll
-          for (int v = 0; v < V; ++v)
-            if (i_first + v >= prm.r0 && i_first + v < prm.r1) orow[v] = res.v[v];
-        }
+            for (int v = 0; v < V; ++v)
+              if (i_first + v >= prm.r0 && i_first + v < prm.r1) orow[v] = res.v[v];
+          }
+        };
+        put(prm.out);
+        if (prm.out2) put(prm.out2);
+        if (prm.out3) put(prm.out3);
       }
     }
     __syncwarp();
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(192, 5) axis_rowtma_kernel(const __grid_consta
 }
 
 template <typename T, int LO, int HI>
-static int launch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done) {
+static int launch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done, T* out2, T* out3) {
   using G = Geo<T, LO, HI>;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return FDX_EUNSUPPORTED;
@@ -232,7 +242,7 @@ static int launch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double
     return FDX_EUNSUPPORTED;
   const int64_t items = (int64_t)((p->n + G::TX - 1) / G::TX) * ((outer + G::TYR - 1) / G::TYR);
   if (items > 0x7fffffffLL) return FDX_EUNSUPPORTED;
-  prm.x = x, prm.out = out, prm.rows = (int)outer, prm.n = p->n, prm.n_v = p->n / G::V, prm.r0 = p->nl, prm.r1 = p->n - p->nr;
+  prm.x = x, prm.out = out, prm.out2 = out2, prm.out3 = out3, prm.rows = (int)outer, prm.n = p->n, prm.n_v = p->n / G::V, prm.r0 = p->nl, prm.r1 = p->n - p->nr;
   prm.strips = (p->n + G::TX - 1) / G::TX;
   prm.items = (int)items;
   prm.b = bands_of(p), prm.alpha = (T)alpha, prm.taps = scaled_taps<T>(p, alpha);
@@ -261,13 +271,13 @@ static int launch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double
 }
 
 template <typename T>
-static int dispatch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done) {
+static int dispatch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done, T* out2, T* out3) {
   const int lo = p->lo, hi = p->hi;
 #define FDX_C(P_) \
-  if (lo == -P_ && hi == P_) return launch<T, -P_, P_>(p, x, out, outer, alpha, st, band_done);
+  if (lo == -P_ && hi == P_) return launch<T, -P_, P_>(p, x, out, outer, alpha, st, band_done, out2, out3);
 #define FDX_F(L_)                                                                        \
-  if (lo == 0 && hi == L_) return launch<T, 0, L_>(p, x, out, outer, alpha, st, band_done); \
-  if (lo == -L_ && hi == 0) return launch<T, -L_, 0>(p, x, out, outer, alpha, st, band_done);
+  if (lo == 0 && hi == L_) return launch<T, 0, L_>(p, x, out, outer, alpha, st, band_done, out2, out3); \
+  if (lo == -L_ && hi == 0) return launch<T, -L_, 0>(p, x, out, outer, alpha, st, band_done, out2, out3);
   FDX_C(1) FDX_C(2) FDX_C(3) FDX_C(4) FDX_C(5) FDX_C(6)
   FDX_F(1) FDX_F(2) FDX_F(3) FDX_F(4) FDX_F(5) FDX_F(6) FDX_F(7) FDX_F(8) FDX_F(9) FDX_F(10) FDX_F(11)
 #undef FDX_C
@@ -280,16 +290,16 @@ static int dispatch(const fdx_plan_s* p, const T* x, T* out, int64_t outer, doub
 // Entry for fdx_axis.cu: FDX_EUNSUPPORTED = not this kernel's case (the caller goes on to axis_row).  Big aligned arrays
 // only: below ~8 MB the L1-gather kernel's short CTAs fill the machine faster than a persistent ring starts up.
 template <typename T>
-int row_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done) {
+int row_tma_apply(const fdx_plan_s* p, const T* x, T* out, int64_t outer, double alpha, cudaStream_t st, bool* band_done, T* out2, T* out3) {
   constexpr int V = 16 / (int)sizeof(T);
   if (env_int("FDX_ROWTMA_DISABLE", 0)) return FDX_EUNSUPPORTED;
-  if (p->n % V != 0 || (((uintptr_t)x | (uintptr_t)out) & 15) != 0) return FDX_EUNSUPPORTED;
+  if (p->n % V != 0 || (((uintptr_t)x | (uintptr_t)out | (uintptr_t)out2 | (uintptr_t)out3) & 15) != 0) return FDX_EUNSUPPORTED;
   if (p->n - p->nl - p->nr <= 0 || outer <= 0 || outer > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   const int64_t bytes = outer * (int64_t)p->n * (int64_t)sizeof(T);
-  if (bytes < (int64_t)env_int("FDX_ROWTMA_MIN_MB", 8) * (1 << 20) || p->n < 4 * 32 * V) return FDX_EUNSUPPORTED;
-  return rowtma::dispatch<T>(p, x, out, outer, alpha, st, band_done);
+  if (bytes < (int64_t)env_int("FDX_ROWTMA_MIN_MB", 8) * (1 << 20) || p->n < 32 * V) return FDX_EUNSUPPORTED;  // (at least one full strip)
+  return rowtma::dispatch<T>(p, x, out, outer, alpha, st, band_done, out2, out3);
 }
-template int row_tma_apply<float>(const fdx_plan_s*, const float*, float*, int64_t, double, cudaStream_t, bool*);
-template int row_tma_apply<double>(const fdx_plan_s*, const double*, double*, int64_t, double, cudaStream_t, bool*);
+template int row_tma_apply<float>(const fdx_plan_s*, const float*, float*, int64_t, double, cudaStream_t, bool*, float*, float*);
+template int row_tma_apply<double>(const fdx_plan_s*, const double*, double*, int64_t, double, cudaStream_t, bool*, double*, double*);
 
 }  // namespace fdx

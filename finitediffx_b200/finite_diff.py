@@ -675,18 +675,18 @@ def hessian(array, *, accuracy=2, step_size=1, method: MethodKind = "central"):
         flat = torch.cat([table[i + j] for i in range(nd) for j in range(nd)], dim=0)
         return restore(flat.reshape((nd, nd) + tuple(x.shape)))
     # no gradient wanted: every surviving entry is computed ONCE, straight into its first slot of the (nd, nd, ...)
-    # result, and copied to the other slots with i + j == key (the reference: nd + nd (nd - 1) differences, each a
-    # concatenate, then nd + 1 stacks).  3-D: 7 axis passes + 4 slot copies instead of 9 passes and two full copies.
+    # result and, by the same pass, into the other slots with i + j == key (fdx_axis_apply_dup: the stores are repeated;
+    # the reference: nd + nd (nd - 1) differences, each a concatenate, then nd + 1 stacks).  3-D: 7 axis passes, no copies.
     for t in [d2(k) for k in range(nd)] + [d1(k) for k in range(nd)]:
         t.plan(x.shape[t.axis])  # the reference's ValueErrors, before anything is launched
     out = torch.empty((nd, nd) + tuple(x.shape), dtype=x.dtype, device=x.device)
     first = {}
     for key, who in producer.items():
         slots = [(i, key - i) for i in range(nd) if 0 <= key - i < nd]
-        dst = out[slots[0]]
+        dsts = [out[sl] for sl in slots]  # (at most three: H[i][j] with i + j == key)
         if len(who) == 1:
             t = d2(who[0])
-            _cabi.axis_apply(t.plan(x.shape[t.axis]), x, dst, t.axis, t.alpha)
+            _cabi.axis_apply_dup(t.plan(x.shape[t.axis]), x, dsts, t.axis, t.alpha)
         else:
             a1, a2 = who
             if a1 not in first:
@@ -694,9 +694,7 @@ def hessian(array, *, accuracy=2, step_size=1, method: MethodKind = "central"):
                 first[a1] = torch.empty_like(x)
                 _cabi.axis_apply(t.plan(x.shape[a1]), x, first[a1], a1, t.alpha)
             t = d1(a2)
-            _cabi.axis_apply(t.plan(x.shape[a2]), first[a1], dst, a2, t.alpha)
-        for sl in slots[1:]:
-            out[sl].copy_(dst)
+            _cabi.axis_apply_dup(t.plan(x.shape[a2]), first[a1], dsts, a2, t.alpha)
     return restore(out)
 
 

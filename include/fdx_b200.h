@@ -70,6 +70,12 @@ int fdx_axis_apply_f32(fdx_plan_t plan, const float* x, float* out, int64_t oute
                        double alpha, int accumulate, void* stream);
 int fdx_axis_apply_f64(fdx_plan_t plan, const double* x, double* out, int64_t outer, int64_t inner,
                        double alpha, int accumulate, void* stream);
+/* The same pass storing its result in up to three arrays of the same shape (out2 / out3 may be NULL): the repeated
+ * entries H[i][j] = F[i + j] of the reference's hessian (finite_diff.py:524-529) without copy passes. */
+int fdx_axis_apply_dup_f32(fdx_plan_t plan, const float* x, float* out, float* out2, float* out3, int64_t outer,
+                           int64_t inner, double alpha, void* stream);
+int fdx_axis_apply_dup_f64(fdx_plan_t plan, const double* x, double* out, double* out2, double* out3, int64_t outer,
+                           int64_t inner, double alpha, void* stream);
 
 /* ---- fused 3-D operators on a C-contiguous (n0, n1, n2) grid; plans[k] acts along axis k and
  * plans[k]->n == n_k.  One pass: every input plane is read once, every output written once.

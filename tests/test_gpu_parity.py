@@ -764,3 +764,28 @@ def test_fused_2d_tma_form_equals_the_plain_form_bit_for_bit(dtype):
                 assert k1.endswith("2d_tma") and k2.endswith("2d"), (op, shape, kw, k1, k2)
                 assert torch.equal(o1, o2), (op, shape, kw, (o1 - o2).abs().max().item())
                 assert torch.equal(g1, g2), (op, shape, kw, "vjp", (g1 - g2).abs().max().item())
+
+
+def test_hessian_on_a_big_grid_one_pass_per_entry_no_copies():
+    """3-D hessian on a grid large enough for the TMA axis kernels: the repeated entries are stored by the producing
+    pass (fdx_axis_apply_dup).  Bit-identical to the small-array path (plain kernels + device copies), and the slots
+    follow the reference's H[i][j] = F[i + j] (oracle parity of the operator itself: test_operators_vs_oracle)."""
+    x = torch.randn((96, 160, 256), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))  # 15.7 MB
+    kw = dict(accuracy=(2, 4, 2), step_size=(0.1, 0.2, 0.3))
+    h = fdx.hessian(x, **kw)
+    assert _cabi.last_kernel() in ("axis_rowtma", "axis_coltma"), _cabi.last_kernel()
+    with _env(FDX_ROWTMA_DISABLE=1, FDX_COLTMA_DISABLE=1):
+        h0 = fdx.hessian(x, **kw)
+        assert _cabi.last_kernel() in ("axis_row", "axis_stream"), _cabi.last_kernel()
+    assert torch.equal(h, h0)
+    for i in range(3):
+        for j in range(3):
+            for k in range(3):
+                for m in range(3):
+                    if i + j == k + m:
+                        assert torch.equal(h[i, j], h[k, m])
+    sub = x[:40, :48, :64].cpu().numpy()
+    ref = O.hessian(sub, **kw)
+    sc = np.abs(ref).max()
+    got = h[:, :, :20, :24, :32].cpu().numpy()
+    assert np.max(np.abs(got - ref[:, :, :20, :24, :32])) <= 2e-4 * sc  # (coarse: the brick's far faces are artificial edges)
