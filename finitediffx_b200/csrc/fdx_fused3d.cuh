@@ -763,8 +763,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
     for (int c = c0; c < c1; ++c) {
       const T cf = prm.tab[tab + c];
       const VT x = lds_vec<T, V>(addr);
-#pragma unroll
-      for (int v = 0; v < V; ++v) a.v[v] = fma(cf, x.v[v], a.v[v]);
+      fma_vec<false>(a, cf, x);  // (packed for fp32: two independent fmas, the bits of the scalar form)
       addr += (uint32_t)pitch_b;
     }
 #pragma unroll
@@ -1113,7 +1112,20 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
       VT zv[Tr::NACC][RY], tin[Tr::NACC][RY], eo[Tr::NACC][RY];
       if (inr) {
         VT ya[NY][RY], xa[NX][RY], ip[NIP + 1][RY];
-        hot_inplane(zv, ya, xa, xe, be);
+        // x bands of the rim copy, single-field operators: the helper-lane form (xband_fast: the owner's RY rows go to RY
+        // neighbouring lanes, ONE pass per warp) instead of RY passes over the owner's register windows -- the tile
+        // runs at the pace of its slowest warp: laplacian 512^3 fp32 -3 % (divergence / curl: no difference, they keep the
+        // register form).  FDX_FUSED_DBG=256 (experiments): the register form everywhere.
+        constexpr bool kRimFast = OP == LAP || OP == GRAD;
+        const bool rimfast = kRimFast && xe && !xcorr && xfast && !(prm.dbg & 256) && (xedge_l || xedge_r);
+        hot_inplane(zv, ya, xa, xe && !rimfast, be);
+        if (rimfast) {
+#pragma unroll
+          for (int qq = 0; qq < NX; ++qq) {
+            const int f = IP::xfield(qq);
+            xband_fast(tb[f] + soff + (uint32_t)(G::yoff(f) * G::box_x(f) * sizeof(T)), G::box_x(f), xa[qq]);
+          }
+        }
         if (xe && xcorr && !(prm.dbg & 64)) {
 #pragma unroll
           for (int qq = 0; qq < NX; ++qq) {
@@ -1122,7 +1134,32 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
           }
         }
         if (ye) {
-          if (yband && !(prm.dbg & 4)) {
+          // y bands of the rim copy.  Dense form with two rows per thread: a thread whose second row is a band row hands
+          // it to the thread two thread-rows further down in its warp (lane ^ 16: same column) when that one has no
+          // band row of its own, and gets the result back with a shuffle -- the three band rows of a warp take ONE pass
+          // instead of two.  Same taps, same order: the bits of band_y_tile.  (FDX_FUSED_DBG=512: one pass per row.)
+          constexpr bool kYShare = RY == 2 && TRW >= 2;
+          if (kYShare && yedge && !ycorr && !(prm.dbg & (4 | 512))) {  // (CTA-uniform: the shuffles see whole warps)
+            const int ygp = y0 + (ty ^ (TRW / 2)) * RY;  // first row of the partner thread
+            auto bandrow = [&](int y) { return y < n1 && (y < A1.nl || y >= n1 - A1.nr); };
+            const bool colok = xg >= x_lo && xg < x_hi;
+            const bool own0 = colok && bandrow(yg), own1 = colok && bandrow(yg + 1);
+            const bool p0 = colok && bandrow(ygp), p1 = colok && bandrow(ygp + 1);
+            const int job = own0 ? yg : (p1 ? ygp + 1 : -1);  // this pass: my first row, else my partner's second row
+#pragma unroll
+            for (int qq = 0; qq < NY; ++qq) {
+              const int f = IP::yfield(qq);
+              const uint32_t tcol = tb[f] + soff - (uint32_t)(ty * RY * G::box_x(f) * (int)sizeof(T));
+              VT val, got;
+#pragma unroll
+              for (int v = 0; v < V; ++v) val.v[v] = 0;
+              if (job >= 0) val = band_y_tile(tcol, G::box_x(f) * (int)sizeof(T), job);
+#pragma unroll
+              for (int v = 0; v < V; ++v) got.v[v] = __shfl_xor_sync(0xffffffffu, val.v[v], 16);
+              if (own0) ya[qq][0] = val;
+              if (own1) ya[qq][1] = p0 ? band_y_tile(tcol, G::box_x(f) * (int)sizeof(T), yg + 1) : got;  // (partner busy: a pass of my own)
+            }
+          } else if (yband && !(prm.dbg & 4)) {
 #pragma unroll
             for (int qq = 0; qq < NY; ++qq) {
               const int f = IP::yfield(qq);
