@@ -486,7 +486,7 @@ def test_specialised_marches_match_the_generic_march_and_the_oracle(dtype):
                 assert _cabi.last_kernel().startswith("fused_"), (op, shape, acc, _cabi.last_kernel())
                 err = parity_error(op, arr, kw, out, getattr(O, op)(arr, **kw))
                 assert err <= TOL[np.dtype(dtype)], (op, shape, acc, err)
-                for env in (dict(FDX_FUSED_NOPLAIN=1), dict(FDX_FUSED_ZB_MERGE=1), dict(FDX_FUSED_RIMFIRST=0), dict(FDX_FUSED_RIMFIRST=1),
+                for env in (dict(FDX_FUSED_NOPLAIN=1), dict(FDX_FUSED_ZB_MERGE=1), dict(FDX_FUSED_RIMFIRST=0), dict(FDX_FUSED_RIMFIRST=1), dict(FDX_FUSED_ZB_LAST=0),
                             dict(FDX_XBAND_NODIRECT=1), dict(FDX_FUSED_CHUNK=5), dict(FDX_FUSED_NOPLAIN=1, FDX_FUSED_ZB_MERGE=1, FDX_FUSED_CHUNK=9)):
                     with _env(**env):
                         other = _call(op, arr, **kw)
