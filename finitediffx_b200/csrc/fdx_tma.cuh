@@ -79,38 +79,43 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// Counter pairs for the item claims, per device: kSlots pairs handed out round-robin, each rewound to zero by the grid
-// that used it (launches on one stream are ordered; more than kSlots launches in flight on different streams would
-// share a pair).  Allocated and zeroed at the first use on a device.
+// Counter pairs for the item claims: a pool per device, ONE pair per stream (handed out at the stream's first launch).
+// Launches on a stream are ordered, so a pair is never used by two grids at once, and the grid that used it rewinds it
+// to zero (the last producer).  Beyond kSlots streams on a device, or inside a stream capture (a captured launch would
+// keep its pair for every replay of the graph, next to later eager launches), the caller takes the non-persistent
+// kernel instead (nullptr).  Allocated and zeroed at the first use on a device.
 unsigned int* claim_slot(cudaStream_t st);  // fdx_rowtma.cu
 #ifdef FDX_TMA_DEFINE_CLAIM_SLOT
 unsigned int* claim_slot(cudaStream_t st) {
   constexpr int kSlots = 256, kDevs = 64;
-  static unsigned int* pool[kDevs] = {nullptr};
-  static std::atomic<unsigned> next{0};
+  struct Pool {
+    unsigned int* base = nullptr;
+    int used = 0;
+    cudaStream_t owner[kSlots];
+  };
+  static Pool pool[kDevs];
   static std::mutex mu;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kDevs) return nullptr;
-  // never inside a stream capture: a captured launch would keep its pair for every replay of the graph, next to eager
-  // launches that are handed the same pair later (the caller then takes the non-persistent kernel)
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
-  unsigned int* base;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    base = pool[dev];
-    if (!base) {
-      if (cudaMalloc(&base, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-      if (cudaMemset(base, 0, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) {
-        cudaFree(base);
-        return nullptr;
-      }
-      pool[dev] = base;
+  std::lock_guard<std::mutex> lk(mu);
+  Pool& p = pool[dev];
+  if (!p.base) {
+    unsigned int* b = nullptr;
+    if (cudaMalloc(&b, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(b, 0, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) {
+      cudaFree(b);
+      return nullptr;
     }
+    p.base = b;
   }
-  return base + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kSlots);
+  for (int i = 0; i < p.used; ++i)
+    if (p.owner[i] == st) return p.base + 2 * i;
+  if (p.used >= kSlots) return nullptr;
+  p.owner[p.used] = st;
+  return p.base + 2 * p.used++;
 }
-
 #endif
 
 }  // namespace tma

@@ -789,3 +789,28 @@ def test_hessian_on_a_big_grid_one_pass_per_entry_no_copies():
     sc = np.abs(ref).max()
     got = h[:, :, :20, :24, :32].cpu().numpy()
     assert np.max(np.abs(got - ref[:, :, :20, :24, :32])) <= 2e-4 * sc  # (coarse: the brick's far faces are artificial edges)
+
+
+def test_big_array_kernels_inside_a_cuda_graph_capture():
+    """The persistent TMA kernels draw their work-claim counters from a pool; a captured launch would keep its pair for
+    every replay, so inside a stream capture the calls take the non-persistent kernels -- same bits, replayable."""
+    x = torch.randn((2304, 1024), device="cuda", generator=torch.Generator(device="cuda").manual_seed(8))  # 9.4 MB
+    kw = dict(accuracy=4, step_size=0.3)
+    eager = [fdx.difference(x, axis=0, derivative=2, **kw), fdx.difference(x, axis=1, derivative=1, **kw), fdx.laplacian(x, **kw)]
+    names = []
+    for call in (lambda: fdx.difference(x, axis=0, derivative=2, **kw), lambda: fdx.difference(x, axis=1, derivative=1, **kw), lambda: fdx.laplacian(x, **kw)):
+        call()
+        names.append(_cabi.last_kernel())
+    assert names == ["axis_coltma", "axis_rowtma", "fused_laplacian2d_tma"], names
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            captured = [fdx.difference(x, axis=0, derivative=2, **kw), fdx.difference(x, axis=1, derivative=1, **kw), fdx.laplacian(x, **kw)]
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(eager, captured):
+        assert torch.equal(a, b)
