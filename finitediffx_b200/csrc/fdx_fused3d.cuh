@@ -1873,6 +1873,8 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
       FDX_CFG(27, 16, 4, 4, 3, 4)      // 64x16 tile, 64 threads, 4 CTAs per SM
       FDX_CFG(28, 16, 8, 4, 3, 2)
       FDX_CFG(29, 16, 4, 4, 4, 3)
+      // fp32: three CTAs per SM with deep rings (how much do 12 instead of 16 warps cost?)
+      FDX_CFG(30, 16, 8, 2, 8, 3, 8)
       default:
         break;
     }
