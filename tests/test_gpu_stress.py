@@ -114,3 +114,16 @@ def test_random_operators_vs_oracle(seed):
         assert err <= TOL[np.dtype(dtype)], (case, op, shape, kw, err)
         done += 1
     assert done == 70
+
+
+def test_random_shapes_through_the_tma_ring_kernels():
+    """tools/stress_tma.py: 200 random `difference` / 2-D operator calls forced through the persistent TMA-ring kernels
+    (all methods, derivative 1-4, accuracy 1-8, 2-D to 4-D arrays, every axis) equal the non-persistent kernels bit for
+    bit (those are the ones checked against the oracle throughout tests/test_gpu_parity.py)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_tma.py"), "200", "11"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
