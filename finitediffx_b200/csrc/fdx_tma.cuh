@@ -79,18 +79,20 @@ inline EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// Counter pairs for the item claims: a pool per device, ONE pair per stream (handed out at the stream's first launch).
-// Launches on a stream are ordered, so a pair is never used by two grids at once, and the grid that used it rewinds it
-// to zero (the last producer).  Beyond kSlots streams on a device, or inside a stream capture (a captured launch would
-// keep its pair for every replay of the graph, next to later eager launches), the caller takes the non-persistent
-// kernel instead (nullptr).  Allocated and zeroed at the first use on a device.
+// Counter pairs for the item claims: a pool per device.  Eager launches: ONE pair per stream (handed out at the
+// stream's first launch) -- launches on a stream are ordered, so a pair is never used by two grids at once, and the grid
+// that used it rewinds it to zero (the last producer).  Launches inside a stream capture: a pair of their own from a
+// second region of the pool (a captured launch keeps its pair for every replay of its graph, so it must not share it
+// with anything; a memset node in front of the kernel zeroes it at every replay).  nullptr -- the caller takes the
+// non-persistent kernel instead -- beyond kSlots streams or kCapture captured launches on a device, or when the very
+// first use on a device happens inside a capture (the pool is allocated and zeroed outside).
 unsigned int* claim_slot(cudaStream_t st);  // fdx_rowtma.cu
 #ifdef FDX_TMA_DEFINE_CLAIM_SLOT
 unsigned int* claim_slot(cudaStream_t st) {
-  constexpr int kSlots = 256, kDevs = 64;
+  constexpr int kSlots = 256, kCapture = 8192, kDevs = 64;
   struct Pool {
     unsigned int* base = nullptr;
-    int used = 0;
+    int used = 0, captured = 0;
     cudaStream_t owner[kSlots];
   };
   static Pool pool[kDevs];
@@ -98,17 +100,27 @@ unsigned int* claim_slot(cudaStream_t st) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kDevs) return nullptr;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) return nullptr;
+  const bool capturing = cs != cudaStreamCaptureStatusNone;
   std::lock_guard<std::mutex> lk(mu);
   Pool& p = pool[dev];
   if (!p.base) {
+    if (capturing) return nullptr;
     unsigned int* b = nullptr;
-    if (cudaMalloc(&b, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    if (cudaMemset(b, 0, kSlots * 2 * sizeof(unsigned int)) != cudaSuccess) {
+    const size_t bytes = (size_t)(kSlots + kCapture) * 2 * sizeof(unsigned int);
+    if (cudaMalloc(&b, bytes) != cudaSuccess) return nullptr;
+    if (cudaMemset(b, 0, bytes) != cudaSuccess) {
       cudaFree(b);
       return nullptr;
     }
     p.base = b;
+  }
+  if (capturing) {
+    if (p.captured >= kCapture) return nullptr;
+    unsigned int* pair = p.base + 2 * (kSlots + p.captured);
+    if (cudaMemsetAsync(pair, 0, 2 * sizeof(unsigned int), st) != cudaSuccess) return nullptr;  // (a node of the graph)
+    ++p.captured;
+    return pair;
   }
   for (int i = 0; i < p.used; ++i)
     if (p.owner[i] == st) return p.base + 2 * i;

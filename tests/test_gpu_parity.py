@@ -792,8 +792,9 @@ def test_hessian_on_a_big_grid_one_pass_per_entry_no_copies():
 
 
 def test_big_array_kernels_inside_a_cuda_graph_capture():
-    """The persistent TMA kernels draw their work-claim counters from a pool; a captured launch would keep its pair for
-    every replay, so inside a stream capture the calls take the non-persistent kernels -- same bits, replayable."""
+    """The persistent TMA kernels draw their work-claim counters from a pool: one pair per stream for eager launches, a
+    pair of its own (zeroed by a memset node at every replay) for a launch inside a stream capture.  Captured calls
+    run the same kernels, give the same bits and can be replayed -- also next to eager launches on the capture stream."""
     x = torch.randn((2304, 1024), device="cuda", generator=torch.Generator(device="cuda").manual_seed(8))  # 9.4 MB
     kw = dict(accuracy=4, step_size=0.3)
     eager = [fdx.difference(x, axis=0, derivative=2, **kw), fdx.difference(x, axis=1, derivative=1, **kw), fdx.laplacian(x, **kw)]
@@ -808,9 +809,15 @@ def test_big_array_kernels_inside_a_cuda_graph_capture():
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
             captured = [fdx.difference(x, axis=0, derivative=2, **kw), fdx.difference(x, axis=1, derivative=1, **kw), fdx.laplacian(x, **kw)]
+            assert _cabi.last_kernel() == "fused_laplacian2d_tma", _cabi.last_kernel()
     torch.cuda.current_stream().wait_stream(side)
-    for _ in range(2):
+    for rep in range(3):
+        for t in captured:
+            t.zero_()
         graph.replay()
-    torch.cuda.synchronize()
-    for a, b in zip(eager, captured):
-        assert torch.equal(a, b)
+        with torch.cuda.stream(side):  # eager launches on the capture stream while the graph runs elsewhere
+            again = fdx.difference(x, axis=1, derivative=1, **kw)
+        torch.cuda.synchronize()
+        for a, b in zip(eager, captured):
+            assert torch.equal(a, b), rep
+        assert torch.equal(again, eager[1])
