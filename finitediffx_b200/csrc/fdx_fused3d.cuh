@@ -132,9 +132,10 @@ struct FusedParams {
 
 // TXV x TYT threads own RY rows x one 16-byte vector each; a warp covers LX x (32 / LX) of them.  A narrow
 // warp (LX < TXV) keeps the x-band work of the first / last tile of a row inside fewer warps.
-template <int TXV_, int TYT_, int RY_, int STAGES_, int MINB_ = 1, int LX_ = 0>
+template <int TXV_, int TYT_, int RY_, int STAGES_, int MINB_ = 1, int LX_ = 0, int PW_ = 0>
 struct Cfg {
   static constexpr int TXV = TXV_, TYT = TYT_, RY = RY_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int PW = PW_;  // (sweeps) a producer warp of its own: the consumers never issue TMA
   static constexpr int LX = LX_ > 0 ? LX_ : (TXV_ < 32 ? TXV_ : 32);
   static_assert(32 % LX == 0 && TXV_ % LX == 0 && TYT_ % (32 / LX) == 0 && LX >= RY_, "warp shape");
 };
@@ -173,7 +174,8 @@ struct Geometry {
   static constexpr int HXV = (P + V - 1) / V;  // halo vectors each side in x
   static constexpr int HX = HXV * V;
   static constexpr int TX = CFG::TXV * V, TY = CFG::TYT * CFG::RY;
-  static constexpr int NT = CFG::TXV * CFG::TYT;  // threads; all of them consume, thread 0 also issues TMA
+  static constexpr int NC = CFG::TXV * CFG::TYT;        // consumer threads
+  static constexpr int NT = NC + (CFG::PW ? 32 : 0);   // threads (without a producer warp: elected consumer lanes issue TMA)
   static constexpr int WZ = 2 * P + 1;
   __host__ __device__ static constexpr int xoff(int f) { return Tr::hx(f) ? HX : 0; }
   __host__ __device__ static constexpr int yoff(int f) { return Tr::hy(f) ? P : 0; }
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init_a(bar_full + 8u * s, 1);
-      mbar_init_a(bar_empty + 8u * s, G::NT / 32);
+      mbar_init_a(bar_empty + 8u * s, G::NC / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -457,16 +459,25 @@ __global__ void __launch_bounds__(Geometry<OP, T, P, CFG>::NT, CFG::MINB)
         tma_prefetch_3d(&prm.tmap[f], x0 - G::xoff(f), y0 - G::yoff(f), zt + prm.l2_ahead);
     }
   };
-  if (tid == 0) {
+  if constexpr (CFG::PW) {
+    // (sweep configurations) the producer warp: one lane issues every plane of the march, as far ahead as the ring allows
+    if (tid >= G::NC) {
+      if (tid == G::NC) {
+        for (int f = 0; f < Tr::NIN; ++f) asm volatile("prefetch.tensormap [%0];" ::"l"(&prm.tmap[f]) : "memory");
+        for (int it = 0; it < n_planes; ++it) issue(it);
+      }
+      return;
+    }
+  } else if (tid == 0) {
     for (int f = 0; f < Tr::NIN; ++f) asm volatile("prefetch.tensormap [%0];" ::"l"(&prm.tmap[f]) : "memory");
     for (int it = 0; it < LOOK && it < n_planes; ++it) issue(it);
   }
   // The issue duty rotates over the warps (lane 0 of warp it % NW issues at step it): the ~35 instructions of an issue
   // are then paid by every warp once in NW steps instead of by warp 0 at every step -- warp 0 was the slowest warp
   // of an interior CTA and the step time of a CTA is that of its slowest warp.  (FDX_ISSUE_ROT=0: thread 0 always.)
-  constexpr int NW = G::NT / 32;
+  constexpr int NW = G::NC / 32;
   const bool rot = prm.issue_rot != 0;
-  auto issuer = [&](int it) { return rot ? (it % NW) * 32 : 0; };
+  auto issuer = [&](int it) { return CFG::PW ? -1 : (rot ? (it % NW) * 32 : 0); };
 
   const int wrp = tid / 32;
   const int tx = (wrp % (CFG::TXV / LX)) * LX + lane % LX, ty = (wrp / (CFG::TXV / LX)) * TRW + lane / LX;
@@ -1875,6 +1886,7 @@ static int launch_p(const fdx_plan_t plans[3], const T* const in[3], T* const ou
       FDX_CFG(29, 16, 4, 4, 4, 3)
       // fp32: three CTAs per SM with deep rings (how much do 12 instead of 16 warps cost?)
       FDX_CFG(30, 16, 8, 2, 8, 3, 8)
+      FDX_CFG(32, 16, 8, 2, 8, 3, 8, 1)  // ... with a producer warp
       default:
         break;
     }
