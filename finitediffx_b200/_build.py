@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(LIBDIR, "libfdx_b200.so")
-SOURCES = ("fdx_plan.cu", "fdx_axis.cu", "fdx_rowtma.cu", "fdx_coltma.cu", "fdx_dev_alpha.cu", "fdx_fused2d.cu", "fdx_fused3d_lap.cu", "fdx_fused3d_div.cu", "fdx_fused3d_grad.cu", "fdx_fused3d_curl.cu")
+SOURCES = ("fdx_plan.cu", "fdx_axis.cu", "fdx_rowtma.cu", "fdx_coltma.cu", "fdx_dev_alpha.cu", "fdx_fused2d.cu", "fdx_hessian3d.cu", "fdx_fused3d_lap.cu", "fdx_fused3d_div.cu", "fdx_fused3d_grad.cu", "fdx_fused3d_curl.cu")
 NVCC_FLAGS = [
     *(["-DFDX_SWEEP"] if os.environ.get("FDX_SWEEP") else []),
     *([f"-DFDX_SWEEP_P={os.environ['FDX_SWEEP_P']}"] if os.environ.get("FDX_SWEEP_P") else []),

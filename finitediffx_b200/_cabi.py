@@ -95,6 +95,8 @@ EXPORTS = (
     "fdx_gradient2d_f64",
     "fdx_axis_apply_dup_f32",
     "fdx_axis_apply_dup_f64",
+    "fdx_hessian3d_f32",
+    "fdx_hessian3d_f64",
 )
 
 
@@ -132,6 +134,7 @@ def load():
         for sfx in ("f32", "f64"):
             getattr(lib, f"fdx_axis_apply_{sfx}").argtypes = [vp, vp, vp, i64, i64, dbl, i32, vp]
             getattr(lib, f"fdx_axis_apply_dup_{sfx}").argtypes = [vp, vp, vp, vp, vp, i64, i64, dbl, vp]
+            getattr(lib, f"fdx_hessian3d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, vp, C.POINTER(dbl), C.POINTER(dbl), vp]
             getattr(lib, f"fdx_laplacian2d_{sfx}").argtypes = [C.POINTER(vp), vp, vp, C.POINTER(dbl), vp]
             getattr(lib, f"fdx_divergence2d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(dbl), vp]
             getattr(lib, f"fdx_gradient2d_{sfx}").argtypes = [C.POINTER(vp), vp, C.POINTER(vp), C.POINTER(dbl), vp]
@@ -295,6 +298,28 @@ def axis_apply_dup(plan: AxisPlan, x: torch.Tensor, outs: Sequence[torch.Tensor]
     with _on_device(x.device):
         fn = getattr(load(), f"fdx_axis_apply_dup_{_sfx(x)}")
         check(fn(dp.handle, C.c_void_p(x.data_ptr()), ptr[0], ptr[1], ptr[2], outer, inner, float(alpha), _stream_ptr(x.device)), "fdx_axis_apply_dup")
+
+
+def hessian3d(d1: Sequence[AxisPlan], d2: Sequence["AxisPlan | None"], x: torch.Tensor, h: torch.Tensor, a1: Sequence[float],
+              a2: Sequence[float]) -> int:
+    """The fused 3-D hessian (reference finite_diff.py:460-529): ``h`` (3, 3, *x.shape) receives F[i + j] in every slot,
+    one pass over ``x``.  ``d1`` / ``d2``: first- / second-derivative plans per axis (``d2[1]`` unused).  Returns the library
+    status: 0, or -2 when the fused kernel does not cover the call (the caller composes axis passes instead)."""
+    _require(x, "x")
+    _require(h, "h")
+    assert x.ndim == 3 and tuple(h.shape) == (3, 3) + tuple(x.shape) and h.dtype == x.dtype
+    if x.numel() == 0:
+        return 0
+    k1 = [device_plan(p, x.device) for p in d1]
+    k2 = [device_plan(p, x.device) if p is not None else None for p in d2]
+    hp1 = (C.c_void_p * 3)(*[dp.handle for dp in k1])
+    hp2 = (C.c_void_p * 3)(*[dp.handle if dp is not None else None for dp in k2])
+    with _on_device(x.device):
+        fn = getattr(load(), f"fdx_hessian3d_{_sfx(x)}")
+        rc = fn(hp1, hp2, C.c_void_p(x.data_ptr()), C.c_void_p(h.data_ptr()), _alphas(a1), _alphas(a2), _stream_ptr(x.device))
+    if rc != 0 and rc != -2:
+        check(rc, "fdx_hessian3d")
+    return rc
 
 
 def axis_apply_dev_alpha(plan: AxisPlan, x: torch.Tensor, out: torch.Tensor, axis: int, alpha_dev: torch.Tensor, sign: float = 1.0,

@@ -1,0 +1,482 @@
+// Fused 3-D hessian: replaces the reference's `hessian` on a 3-D scalar field (finitediffx/_src/finite_diff.py:460-529:
+// ndim second differences + ndim (ndim - 1) / 2 nested first differences, each a `concatenate`, then ndim + 1 `stack`s)
+// by ONE pass over the input: 1 read + 9 writes per point (10 s bytes; the composition of axis passes moves 18 s).
+//
+// The reference's result table is F[ax1 + ax2] (:499, :510), so for ndim = 3 the five surviving entries are
+//   F[0] = D2_0 x,  F[1] = D_1 D_0 x,  F[2] = D_2 D_0 x (it replaces D2_1 x: SURVEY F4),  F[3] = D_2 D_1 x,  F[4] = D2_2 x
+// and H[i][j] = F[i + j] (:524-529).  This kernel produces exactly those five fields and stores each of them in every
+// slot (i, j) with i + j = key of the (3, 3, n0, n1, n2) result.
+//
+// Two launches:
+//   hessian3d_kernel   the points whose rows are main rows on all three axes.  There the nested differences are pure
+//                      tensor products of the main stencils (operators on different axes commute), so a CTA marches a
+//                      (8 x 32 vectors) tile along axis 0: plane z is staged in shared memory (cp.async, zero fill outside
+//                      the grid, double buffered), a first stage writes gx = D_2 x of the tile and its y halo rows to
+//                      shared memory, the second stage gives every thread D2_2 x, gy = D_1 x and D_1 gx of its vector, and
+//                      three shift-register queues along z (x -> D2_0 x, gy -> D_0 D_1 x, gx -> D_0 D_2 x) complete
+//                      planes z - P2 / z - P1.  All taps sit in the parameter block pre-multiplied by the scales.
+//   hessian3d_shell    the boundary shell (points in a band row of any axis: the reference's one-sided rows,
+//                      finite_diff.py:75-88): nested dense gathers with the plans' band tables, accumulated in float64.
+//                      It runs after the main launch on the same stream and overwrites the shell points of its tiles.
+#include <algorithm>
+
+#include "fdx_common.cuh"
+
+namespace fdx {
+namespace {
+
+// P1 = reach of the first-derivative stencils (all three axes), P2 = P1 + 1 = reach of the second-derivative stencils
+// (axes 0 and 2): at equal accuracy the reference's second-derivative stencil is one point longer on each side
+// (utils.py:59-79 through finite_diff.py:247-258); shorter plans are padded with zero taps.
+template <typename T, int P1>
+struct HessGeom {
+  static constexpr int V = 16 / (int)sizeof(T);
+  static constexpr int P2 = P1 + 1;
+  static constexpr int W1 = 2 * P1 + 1, W2 = 2 * P2 + 1;
+  static constexpr int HXV = (P2 + V - 1) / V;  // halo vectors per side
+  static constexpr int HX = HXV * V;
+  static constexpr int TXV = 32, TX = TXV * V, TY = 8;
+  static constexpr int ROWS = TY + 2 * P1;
+  static constexpr int XSV = TXV + 2 * HXV;  // vectors per staged row
+  static constexpr int WV = 1 + 2 * HXV;     // vectors of a thread's x window
+  static constexpr int XS_ELEMS = ROWS * XSV * V;
+  static constexpr int GS_ELEMS = ROWS * TX;
+  static constexpr int NT = 256;
+  static constexpr int NLD = (ROWS * XSV + NT - 1) / NT;
+  static constexpr int NGX = (ROWS * TXV + NT - 1) / NT;
+};
+
+template <typename T, int P1>
+struct HessParams {
+  const T* x;
+  T* h;  // (3, 3, n0, n1, n2)
+  int32_t n0, n1, n2;
+  int32_t z_lo, z_hi;  // output planes of the main launch
+  int32_t zc;          // planes per chunk
+  int32_t tiles_x, tiles_y;
+  // radius-P2 / radius-P1 taps (zero where a plan is shorter), scales folded in
+  T c2z[2 * P1 + 3], c2x[2 * P1 + 3], c1z[2 * P1 + 1], c1y[2 * P1 + 1], c1x[2 * P1 + 1];
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename T, int V>
+__device__ __forceinline__ void st_cs(T* p, const Vec<T, V>& r) {
+  if constexpr (sizeof(T) == 4) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+  } else {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(r.v[0], r.v[1]));
+  }
+}
+
+template <typename T, int P1, int MINB>
+__global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_constant__ HessParams<T, P1> prm) {
+  using G = HessGeom<T, P1>;
+  constexpr int V = G::V, P2 = G::P2, W1 = G::W1, W2 = G::W2, HX = G::HX, HXV = G::HXV, XSV = G::XSV, TX = G::TX;
+  using VecT = Vec<T, V>;
+  __shared__ __align__(16) T xs[2][G::XS_ELEMS];
+  __shared__ __align__(16) T gs[G::GS_ELEMS];
+
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  int b = blockIdx.x;
+  const int tx = b % prm.tiles_x;
+  b /= prm.tiles_x;
+  const int ty = b % prm.tiles_y;
+  b /= prm.tiles_y;
+  const int zc0 = prm.z_lo + b * prm.zc, zc1 = min(zc0 + prm.zc, prm.z_hi);
+  const int x0 = tx * TX, y0 = ty * G::TY;
+  const int64_t plane = (int64_t)prm.n1 * prm.n2;
+  const int64_t N = plane * prm.n0;
+
+  // what this thread stages of every plane (the same slots for all planes)
+  int goff[G::NLD], soff[G::NLD];
+  bool ok[G::NLD];
+#pragma unroll
+  for (int s = 0; s < G::NLD; ++s) {
+    const int idx = tid + s * G::NT;
+    soff[s] = -1, goff[s] = 0, ok[s] = false;
+    if (idx < G::ROWS * XSV) {
+      const int r = idx / XSV, v = idx - r * XSV;
+      const int yy = y0 - P1 + r, xx = x0 - HX + v * V;
+      soff[s] = idx * V;
+      ok[s] = yy >= 0 && yy < prm.n1 && xx >= 0 && xx < prm.n2;
+      goff[s] = ok[s] ? yy * prm.n2 + xx : 0;
+    }
+  }
+  auto stage = [&](int z, int buf) {
+    const bool zin = z >= 0 && z < prm.n0;
+    const T* src = prm.x + (zin ? (int64_t)z * plane : 0);
+#pragma unroll
+    for (int s = 0; s < G::NLD; ++s)
+      if (soff[s] >= 0) cp_async16(&xs[buf][soff[s]], src + goff[s], zin && ok[s]);
+  };
+
+  // own vector
+  const int yo = y0 + wrp, xo = x0 + lane * V;
+  const bool own = yo < prm.n1 && xo < prm.n2;
+  const int64_t ooff = (int64_t)yo * prm.n2 + xo;
+
+  T q0[2 * P2][V], q1[2 * P1][V], q2[2 * P1][V];
+#pragma unroll
+  for (int j = 0; j < 2 * P2; ++j)
+#pragma unroll
+    for (int p = 0; p < V; ++p) q0[j][p] = (T)0;
+#pragma unroll
+  for (int j = 0; j < 2 * P1; ++j)
+#pragma unroll
+    for (int p = 0; p < V; ++p) q1[j][p] = q2[j][p] = (T)0;
+
+  const int zfirst = zc0 - P2, zlast = zc1 - 1 + P2;
+  stage(zfirst, 0);
+  for (int z = zfirst; z <= zlast; ++z) {
+    const int cur = (z - zfirst) & 1;
+    cp_async_commit_wait_all();
+    __syncthreads();
+    if (z < zlast) stage(z + 1, cur ^ 1);
+    const T* X = xs[cur];
+
+    // ---- stage B: gx = D_2 x on the tile rows and their y halo
+#pragma unroll
+    for (int s = 0; s < G::NGX; ++s) {
+      const int r = wrp + s * 8;
+      if (r < G::ROWS) {
+        T w[G::WV * V];
+#pragma unroll
+        for (int u = 0; u < G::WV; ++u) {
+          const VecT t = *reinterpret_cast<const VecT*>(&X[(r * XSV + lane + u) * V]);
+#pragma unroll
+          for (int p = 0; p < V; ++p) w[u * V + p] = t.v[p];
+        }
+        VecT g;
+#pragma unroll
+        for (int p = 0; p < V; ++p) {
+          T a = (T)0;
+#pragma unroll
+          for (int k = 0; k < W1; ++k) a = fma(prm.c1x[k], w[HX - P1 + p + k], a);
+          g.v[p] = a;
+        }
+        *reinterpret_cast<VecT*>(&gs[r * TX + lane * V]) = g;
+      }
+    }
+    __syncthreads();
+
+    // ---- stage C: the thread's own vector of plane z
+    const bool inplane = z >= zc0 && z < zc1;
+    T xc[V], gyv[V], gxc[V];
+    {
+      T w[G::WV * V];
+      const int r = wrp + P1;
+#pragma unroll
+      for (int u = 0; u < G::WV; ++u) {
+        const VecT t = *reinterpret_cast<const VecT*>(&X[(r * XSV + lane + u) * V]);
+#pragma unroll
+        for (int p = 0; p < V; ++p) w[u * V + p] = t.v[p];
+      }
+#pragma unroll
+      for (int p = 0; p < V; ++p) xc[p] = w[HX + p];
+      VecT d22, d12;
+#pragma unroll
+      for (int p = 0; p < V; ++p) {
+        T a = (T)0;
+#pragma unroll
+        for (int k = 0; k < W2; ++k) a = fma(prm.c2x[k], w[HX - P2 + p + k], a);
+        d22.v[p] = a;
+        gyv[p] = (T)0, d12.v[p] = (T)0;
+      }
+#pragma unroll
+      for (int j = 0; j < W1; ++j) {
+        const VecT gj = *reinterpret_cast<const VecT*>(&gs[(wrp + j) * TX + lane * V]);
+        VecT xj;
+        if (j == P1) {
+#pragma unroll
+          for (int p = 0; p < V; ++p) xj.v[p] = xc[p], gxc[p] = gj.v[p];
+        } else {
+          xj = *reinterpret_cast<const VecT*>(&X[((wrp + j) * XSV + lane + HXV) * V]);
+        }
+#pragma unroll
+        for (int p = 0; p < V; ++p) {
+          gyv[p] = fma(prm.c1y[j], xj.v[p], gyv[p]);
+          d12.v[p] = fma(prm.c1y[j], gj.v[p], d12.v[p]);
+        }
+      }
+      if (inplane && own) {
+        T* o = prm.h + (int64_t)z * plane + ooff;
+        st_cs<T, V>(o + 8 * N, d22);  // key 4: (2,2)
+        st_cs<T, V>(o + 5 * N, d12);  // key 3: (1,2), (2,1)
+        st_cs<T, V>(o + 7 * N, d12);
+      }
+    }
+    // ---- z queues: plane z completes D2_0 x of plane z - P2 and the mixed entries of plane z - P1
+    VecT d00, d01, d02;
+#pragma unroll
+    for (int p = 0; p < V; ++p) {
+      d00.v[p] = fma(prm.c2z[2 * P2], xc[p], q0[0][p]);
+      d01.v[p] = fma(prm.c1z[2 * P1], gyv[p], q1[0][p]);
+      d02.v[p] = fma(prm.c1z[2 * P1], gxc[p], q2[0][p]);
+    }
+#pragma unroll
+    for (int j = 1; j < 2 * P2; ++j)
+#pragma unroll
+      for (int p = 0; p < V; ++p) q0[j - 1][p] = fma(prm.c2z[2 * P2 - j], xc[p], q0[j][p]);
+#pragma unroll
+    for (int j = 1; j < 2 * P1; ++j)
+#pragma unroll
+      for (int p = 0; p < V; ++p) {
+        q1[j - 1][p] = fma(prm.c1z[2 * P1 - j], gyv[p], q1[j][p]);
+        q2[j - 1][p] = fma(prm.c1z[2 * P1 - j], gxc[p], q2[j][p]);
+      }
+#pragma unroll
+    for (int p = 0; p < V; ++p) {
+      q0[2 * P2 - 1][p] = prm.c2z[0] * xc[p];
+      q1[2 * P1 - 1][p] = prm.c1z[0] * gyv[p];
+      q2[2 * P1 - 1][p] = prm.c1z[0] * gxc[p];
+    }
+    const int zo2 = z - P2, zo = z - P1;
+    if (zo2 >= zc0 && zo2 < zc1 && own) st_cs<T, V>(prm.h + (int64_t)zo2 * plane + ooff, d00);  // key 0: (0,0)
+    if (zo >= zc0 && zo < zc1 && own) {
+      T* o = prm.h + (int64_t)zo * plane + ooff;
+      st_cs<T, V>(o + 1 * N, d01);  // key 1: (0,1), (1,0)
+      st_cs<T, V>(o + 3 * N, d01);
+      st_cs<T, V>(o + 2 * N, d02);  // key 2: (0,2), (1,1), (2,0)
+      st_cs<T, V>(o + 4 * N, d02);
+      st_cs<T, V>(o + 6 * N, d02);
+    }
+  }
+}
+
+// ---- boundary shell -------------------------------------------------------------------------------------------------
+struct AxisTab {
+  const double* bl;
+  const double* br;
+  int32_t n, lo, hi, nl, wl, nr, wr;
+  double main[FDX_MAX_TAPS];
+};
+struct RowOp {
+  const double* c;  // band row, or nullptr for the main taps
+  int32_t s, cnt;
+};
+__device__ __forceinline__ RowOp row_of(const AxisTab& a, int i) {
+  if (i < a.nl) return RowOp{a.bl + (int64_t)i * a.wl, 0, a.wl};
+  if (i >= a.n - a.nr) return RowOp{a.br + (int64_t)(i - (a.n - a.nr)) * a.wr, a.n - a.wr, a.wr};
+  return RowOp{nullptr, i + a.lo, a.hi - a.lo + 1};
+}
+__device__ __forceinline__ double tap_of(const AxisTab& a, const RowOp& r, int k) { return r.c ? r.c[k] : a.main[k]; }
+
+template <typename T>
+struct ShellParams {
+  const T* x;
+  T* h;
+  int32_t n0, n1, n2;
+  int32_t bz0, bz1, by0, by1, bx0, bx1;  // main (band-free) index ranges per axis
+  int64_t cnt_a, cnt_b, cnt_c;
+  double s00, s22, s01, s02, s12;  // scales of the five entries
+  AxisTab d1z, d1y, d1x, d2z, d2x;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) hessian3d_shell(const __grid_constant__ ShellParams<T> prm) {
+  int64_t idx = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  int z, y, x;
+  const int nzb = prm.n0 - (prm.bz1 - prm.bz0), nyb = prm.n1 - (prm.by1 - prm.by0), nxb = prm.n2 - (prm.bx1 - prm.bx0);
+  if (idx < prm.cnt_a) {  // band planes of axis 0, whole planes
+    const int64_t pl = (int64_t)prm.n1 * prm.n2;
+    const int zi = (int)(idx / pl);
+    const int64_t rem = idx - (int64_t)zi * pl;
+    z = zi < prm.bz0 ? zi : prm.bz1 + (zi - prm.bz0);
+    y = (int)(rem / prm.n2), x = (int)(rem - (int64_t)y * prm.n2);
+    (void)nzb;
+  } else if (idx < prm.cnt_a + prm.cnt_b) {  // main planes, band rows of axis 1
+    idx -= prm.cnt_a;
+    const int64_t pl = (int64_t)nyb * prm.n2;
+    const int zi = (int)(idx / pl);
+    const int64_t rem = idx - (int64_t)zi * pl;
+    const int yi = (int)(rem / prm.n2);
+    z = prm.bz0 + zi;
+    y = yi < prm.by0 ? yi : prm.by1 + (yi - prm.by0);
+    x = (int)(rem - (int64_t)yi * prm.n2);
+  } else if (idx < prm.cnt_a + prm.cnt_b + prm.cnt_c) {  // main planes and rows, band columns of axis 2
+    idx -= prm.cnt_a + prm.cnt_b;
+    const int64_t pl = (int64_t)(prm.by1 - prm.by0) * nxb;
+    const int zi = (int)(idx / pl);
+    const int64_t rem = idx - (int64_t)zi * pl;
+    const int yi = (int)(rem / nxb), xi = (int)(rem - (int64_t)yi * nxb);
+    z = prm.bz0 + zi, y = prm.by0 + yi;
+    x = xi < prm.bx0 ? xi : prm.bx1 + (xi - prm.bx0);
+  } else {
+    return;
+  }
+  const int64_t s1 = prm.n2, s0 = (int64_t)prm.n1 * prm.n2, N = s0 * prm.n0;
+  const T* X = prm.x;
+  const int64_t at = (int64_t)z * s0 + (int64_t)y * s1 + x;
+
+  const RowOp rz = row_of(prm.d1z, z), ry = row_of(prm.d1y, y), rx = row_of(prm.d1x, x);
+  const RowOp rz2 = row_of(prm.d2z, z), rx2 = row_of(prm.d2x, x);
+  double d00 = 0, d22 = 0, d01 = 0, d02 = 0, d12 = 0;
+  for (int k = 0; k < rz2.cnt; ++k) {
+    const double c = tap_of(prm.d2z, rz2, k);
+    if (c != 0.0) d00 = fma(c, (double)X[(int64_t)(rz2.s + k) * s0 + (int64_t)y * s1 + x], d00);
+  }
+  for (int k = 0; k < rx2.cnt; ++k) {
+    const double c = tap_of(prm.d2x, rx2, k);
+    if (c != 0.0) d22 = fma(c, (double)X[(int64_t)z * s0 + (int64_t)y * s1 + rx2.s + k], d22);
+  }
+  for (int k = 0; k < rz.cnt; ++k) {
+    const double cz = tap_of(prm.d1z, rz, k);
+    if (cz == 0.0) continue;
+    const T* pz = X + (int64_t)(rz.s + k) * s0;
+    double gy = 0, gx = 0;
+    for (int j = 0; j < ry.cnt; ++j) {
+      const double c = tap_of(prm.d1y, ry, j);
+      if (c != 0.0) gy = fma(c, (double)pz[(int64_t)(ry.s + j) * s1 + x], gy);
+    }
+    for (int i = 0; i < rx.cnt; ++i) {
+      const double c = tap_of(prm.d1x, rx, i);
+      if (c != 0.0) gx = fma(c, (double)pz[(int64_t)y * s1 + rx.s + i], gx);
+    }
+    d01 = fma(cz, gy, d01);
+    d02 = fma(cz, gx, d02);
+  }
+  for (int j = 0; j < ry.cnt; ++j) {
+    const double cy = tap_of(prm.d1y, ry, j);
+    if (cy == 0.0) continue;
+    const T* py = X + (int64_t)z * s0 + (int64_t)(ry.s + j) * s1;
+    double gx = 0;
+    for (int i = 0; i < rx.cnt; ++i) {
+      const double c = tap_of(prm.d1x, rx, i);
+      if (c != 0.0) gx = fma(c, (double)py[rx.s + i], gx);
+    }
+    d12 = fma(cy, gx, d12);
+  }
+  T* o = prm.h + at;
+  const T v0 = (T)(d00 * prm.s00), v1 = (T)(d01 * prm.s01), v2 = (T)(d02 * prm.s02), v3 = (T)(d12 * prm.s12), v4 = (T)(d22 * prm.s22);
+  o[0] = v0;
+  o[1 * N] = v1, o[3 * N] = v1;
+  o[2 * N] = v2, o[4 * N] = v2, o[6 * N] = v2;
+  o[5 * N] = v3, o[7 * N] = v3;
+  o[8 * N] = v4;
+}
+
+inline AxisTab tab_of(const fdx_plan_s* p) {
+  AxisTab a;
+  a.bl = p->band_l, a.br = p->band_r;
+  a.n = p->n, a.lo = p->lo, a.hi = p->hi, a.nl = p->nl, a.wl = p->wl, a.nr = p->nr, a.wr = p->wr;
+  for (int k = 0; k < FDX_MAX_TAPS; ++k) a.main[k] = p->main_taps[k];
+  return a;
+}
+
+template <typename T, int P>
+void fill_taps(T (&c)[2 * P + 1], const fdx_plan_s* p, double scale) {  // (P: the radius the kernel runs this stencil at)
+  for (int t = 0; t < 2 * P + 1; ++t) {
+    const int o = t - P;
+    c[t] = (o >= p->lo && o <= p->hi) ? (T)(p->main_taps[o - p->lo] * scale) : (T)0;
+  }
+}
+
+template <typename T, int P1>
+int launch_hess(const fdx_plan_s* const d1[3], const fdx_plan_s* d2z, const fdx_plan_s* d2x, const T* x, T* h, const double a1[3],
+                double a2z, double a2x, const ShellParams<T>& sh, cudaStream_t st) {
+  using G = HessGeom<T, P1>;
+  HessParams<T, P1> prm;
+  prm.x = x, prm.h = h;
+  prm.n0 = sh.n0, prm.n1 = sh.n1, prm.n2 = sh.n2;
+  prm.z_lo = sh.bz0, prm.z_hi = sh.bz1;
+  fill_taps<T, P1 + 1>(prm.c2z, d2z, a2z);
+  fill_taps<T, P1 + 1>(prm.c2x, d2x, a2x);
+  fill_taps<T, P1>(prm.c1z, d1[0], a1[0]);
+  fill_taps<T, P1>(prm.c1y, d1[1], a1[1]);
+  fill_taps<T, P1>(prm.c1x, d1[2], a1[2]);
+  prm.tiles_x = (sh.n2 + G::TX - 1) / G::TX, prm.tiles_y = (sh.n1 + G::TY - 1) / G::TY;
+  const int nz = sh.bz1 - sh.bz0;
+  const bool interior = sh.by1 > sh.by0 && sh.bx1 > sh.bx0 && nz > 0;
+  if (interior) {
+    const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
+    // z chunks: ~8 CTAs per SM over the launch (a chunk re-reads 2 P2 planes), at least 16 planes each
+    int zc = env_int("FDX_HESS_ZC", 0);
+    if (zc <= 0) {
+      const int64_t chunks = std::max<int64_t>(1, ((int64_t)env_int("FDX_HESS_CPS", 8) * num_sms() + tiles - 1) / tiles);
+      zc = (int)((nz + chunks - 1) / chunks);
+      zc = std::max(zc, 16);
+    }
+    zc = std::min(zc, nz);
+    prm.zc = zc;
+    const int64_t blocks = tiles * ((nz + zc - 1) / zc);
+    if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
+    hessian3d_kernel<T, P1, (P1 <= 1 ? 3 : 2)><<<(unsigned)blocks, G::NT, 0, st>>>(prm);
+    count_launch("fused_hessian3d");
+    FDX_LAUNCH_CHECK();
+  }
+  const int64_t pts = sh.cnt_a + sh.cnt_b + sh.cnt_c;
+  if (pts > 0) {
+    const int64_t blocks = (pts + 127) / 128;
+    if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
+    hessian3d_shell<T><<<(unsigned)blocks, 128, 0, st>>>(sh);
+    count_launch("fused_hessian3d");
+    FDX_LAUNCH_CHECK();
+  }
+  return FDX_OK;
+}
+
+template <typename T>
+int run_hess(const fdx_plan_t d1_in[3], const fdx_plan_t d2_in[3], const T* x, T* h, const double a1[3], const double a2[3], void* stream) {
+  constexpr int V = 16 / (int)sizeof(T);
+  if (!d1_in || !d2_in || !a1 || !a2 || !x || !h) return FDX_EINVAL;
+  if (!d1_in[0] || !d1_in[1] || !d1_in[2] || !d2_in[0] || !d2_in[2]) return FDX_EINVAL;
+  if (env_int("FDX_HESS_DISABLE", 0)) return FDX_EUNSUPPORTED;  // (tests: the composition of axis passes instead)
+  const fdx_plan_s* d1[3] = {d1_in[0], d1_in[1], d1_in[2]};
+  const fdx_plan_s *d2z = d2_in[0], *d2x = d2_in[2];
+  if (d2z->n != d1[0]->n || d2x->n != d1[2]->n) return FDX_EINVAL;
+  const int n0 = d1[0]->n, n1 = d1[1]->n, n2 = d1[2]->n;
+  if (n0 == 0 || n1 == 0 || n2 == 0) return FDX_OK;
+  const fdx_plan_s* all[5] = {d1[0], d1[1], d1[2], d2z, d2x};
+  int P1 = 1;
+  for (int k = 0; k < 5; ++k) {
+    const fdx_plan_s* p = all[k];
+    if (p->nl + p->nr > p->n) return FDX_EUNSUPPORTED;  // dense (tiny-n) plans: composition
+    if (p->nl < -p->lo || p->nr < p->hi) return FDX_EUNSUPPORTED;
+    if (p->wl > p->n || p->wr > p->n) return FDX_EUNSUPPORTED;
+    const int reach = std::max(std::abs(p->lo), std::abs(p->hi));
+    P1 = std::max(P1, k < 3 ? reach : reach - 1);  // the kernel runs the second derivatives at radius P1 + 1
+  }
+  if (P1 > 3) return FDX_EUNSUPPORTED;
+  if (n2 % V != 0 || ((uintptr_t)x & 15) != 0 || ((uintptr_t)h & 15) != 0) return FDX_EUNSUPPORTED;
+  if ((int64_t)n1 * n2 >= 0x7fffffffLL) return FDX_EUNSUPPORTED;
+  if (((int64_t)n0 * n1 * n2) % V != 0) return FDX_EUNSUPPORTED;
+
+  ShellParams<T> sh;
+  sh.x = x, sh.h = h, sh.n0 = n0, sh.n1 = n1, sh.n2 = n2;
+  sh.bz0 = std::max(d1[0]->nl, d2z->nl), sh.bz1 = n0 - std::max(d1[0]->nr, d2z->nr);
+  sh.by0 = d1[1]->nl, sh.by1 = n1 - d1[1]->nr;
+  sh.bx0 = std::max(d1[2]->nl, d2x->nl), sh.bx1 = n2 - std::max(d1[2]->nr, d2x->nr);
+  if (sh.bz1 < sh.bz0) sh.bz1 = sh.bz0;
+  if (sh.by1 < sh.by0) sh.by1 = sh.by0;
+  if (sh.bx1 < sh.bx0) sh.bx1 = sh.bx0;
+  const int64_t mz = sh.bz1 - sh.bz0, my = sh.by1 - sh.by0, mx = sh.bx1 - sh.bx0;
+  sh.cnt_a = (int64_t)(n0 - mz) * n1 * n2;
+  sh.cnt_b = mz * (n1 - my) * n2;
+  sh.cnt_c = mz * my * (n2 - mx);
+  sh.s00 = a2[0], sh.s22 = a2[2], sh.s01 = a1[0] * a1[1], sh.s02 = a1[0] * a1[2], sh.s12 = a1[1] * a1[2];
+  sh.d1z = tab_of(d1[0]), sh.d1y = tab_of(d1[1]), sh.d1x = tab_of(d1[2]), sh.d2z = tab_of(d2z), sh.d2x = tab_of(d2x);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (P1) {
+    case 1: return launch_hess<T, 1>(d1, d2z, d2x, x, h, a1, a2[0], a2[2], sh, st);
+    case 2: return launch_hess<T, 2>(d1, d2z, d2x, x, h, a1, a2[0], a2[2], sh, st);
+    default: return launch_hess<T, 3>(d1, d2z, d2x, x, h, a1, a2[0], a2[2], sh, st);
+  }
+}
+
+}  // namespace
+}  // namespace fdx
+
+extern "C" int fdx_hessian3d_f32(const fdx_plan_t d1[3], const fdx_plan_t d2[3], const float* x, float* h, const double a1[3],
+                                 const double a2[3], void* stream) {
+  return fdx::run_hess<float>(d1, d2, x, h, a1, a2, stream);
+}
+extern "C" int fdx_hessian3d_f64(const fdx_plan_t d1[3], const fdx_plan_t d2[3], const double* x, double* h, const double a1[3],
+                                 const double a2[3], void* stream) {
+  return fdx::run_hess<double>(d1, d2, x, h, a1, a2, stream);
+}

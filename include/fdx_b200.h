@@ -143,6 +143,19 @@ int fdx_divergence2d_f64(const fdx_plan_t plans[2], const double* const x[2], do
 int fdx_gradient2d_f32(const fdx_plan_t plans[2], const float* x, float* const out[2], const double alpha[2], void* stream);
 int fdx_gradient2d_f64(const fdx_plan_t plans[2], const double* x, double* const out[2], const double alpha[2], void* stream);
 
+/* ---- fused 3-D hessian of a scalar field (finite_diff.py:460-529), one pass: 1 read + 9 writes per point.
+ * d1[k] / d2[k]: the first- / second-derivative plan along axis k (d2[1] is not used and may be NULL: the reference's
+ * table F[ax1 + ax2] (:499, :510) lets the mixed entry (0, 2) replace the diagonal entry of axis 1).
+ * h is the (3, 3, n0, n1, n2) result; every slot H[i][j] receives F[i + j] (:524-529) with
+ *   F[0] = a2[0] D2_0 x, F[1] = a1[0] a1[1] D_1 D_0 x, F[2] = a1[0] a1[2] D_2 D_0 x, F[3] = a1[1] a1[2] D_2 D_1 x,
+ *   F[4] = a2[2] D2_2 x    (nested differences keep the boundary rows of both plans, as `difference(difference(.))` does).
+ * FDX_EUNSUPPORTED (compose fdx_axis_apply_dup instead) for first-derivative reach > 3 (second-derivative reach > 4), n2 not a multiple of the 16-byte vector,
+ * unaligned pointers and dense tiny-n plans. */
+int fdx_hessian3d_f32(const fdx_plan_t d1[3], const fdx_plan_t d2[3], const float* x, float* h, const double a1[3],
+                      const double a2[3], void* stream);
+int fdx_hessian3d_f64(const fdx_plan_t d1[3], const fdx_plan_t d2[3], const double* x, double* h, const double a1[3],
+                      const double a2[3], void* stream);
+
 /* ---- scale read on the device.  The reference traces `step_size` (finite_diff.py:168), so inside a jitted caller
  * alpha = 1 / step_size**derivative is a DEVICE value; an XLA custom call must not fetch it.  `alpha_dev` is a device
  * pointer to float64: one value for the axis operator (out = sign * alpha_dev[0] * D x), three (one per axis) for the

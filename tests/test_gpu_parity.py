@@ -772,11 +772,12 @@ def test_hessian_on_a_big_grid_one_pass_per_entry_no_copies():
     follow the reference's H[i][j] = F[i + j] (oracle parity of the operator itself: test_operators_vs_oracle)."""
     x = torch.randn((96, 160, 256), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))  # 15.7 MB
     kw = dict(accuracy=(2, 4, 2), step_size=(0.1, 0.2, 0.3))
-    h = fdx.hessian(x, **kw)
-    assert _cabi.last_kernel() in ("axis_rowtma", "axis_coltma"), _cabi.last_kernel()
-    with _env(FDX_ROWTMA_DISABLE=1, FDX_COLTMA_DISABLE=1):
-        h0 = fdx.hessian(x, **kw)
-        assert _cabi.last_kernel() in ("axis_row", "axis_stream"), _cabi.last_kernel()
+    with _env(FDX_HESS_DISABLE=1):  # (the 3-D default is the one-pass fused kernel: test_fused_hessian3d_*)
+        h = fdx.hessian(x, **kw)
+        assert _cabi.last_kernel() in ("axis_rowtma", "axis_coltma"), _cabi.last_kernel()
+        with _env(FDX_ROWTMA_DISABLE=1, FDX_COLTMA_DISABLE=1):
+            h0 = fdx.hessian(x, **kw)
+            assert _cabi.last_kernel() in ("axis_row", "axis_stream"), _cabi.last_kernel()
     assert torch.equal(h, h0)
     for i in range(3):
         for j in range(3):
@@ -789,6 +790,69 @@ def test_hessian_on_a_big_grid_one_pass_per_entry_no_copies():
     sc = np.abs(ref).max()
     got = h[:, :, :20, :24, :32].cpu().numpy()
     assert np.max(np.abs(got - ref[:, :, :20, :24, :32])) <= 2e-4 * sc  # (coarse: the brick's far faces are artificial edges)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_hessian3d_vs_oracle(dtype):
+    """The one-pass 3-D hessian (fdx_hessian3d: main kernel + boundary shell) against the oracle's restatement of
+    finite_diff.py:460-529 (bug-compatible F[ax1 + ax2] table): all three methods, the accuracies the kernel covers, per-axis
+    accuracy and step size, shapes that are no multiple of the tile and shapes of a single tile."""
+    rng = np.random.default_rng(11)
+    cases = [
+        ((20, 22, 24), dict(accuracy=2, step_size=(0.1, 0.2, 0.3))),
+        ((37, 29, 136), dict(accuracy=2, step_size=0.5)),              # two x tiles in fp32, three in fp64
+        ((33, 41, 44), dict(accuracy=4, step_size=(0.1, 0.2, 0.3))),    # reach 2 / 3
+        ((26, 30, 40), dict(accuracy=3, step_size=0.25)),
+        ((30, 27, 36), dict(accuracy=6, step_size=0.5)),                # reach 3 / 4
+        ((30, 27, 36), dict(accuracy=(2, 6, 4), step_size=(0.3, 0.2, 0.1))),
+        ((28, 30, 32), dict(accuracy=(4, 2, 2), step_size=1.0)),
+        ((70, 19, 20), dict(accuracy=2, step_size=0.1)),                # several z chunks (FDX_HESS_ZC below)
+    ]
+    for method in ("central", "forward", "backward"):
+        for shape, kw in cases:
+            acc = kw["accuracy"]
+            amax = max(acc) if isinstance(acc, tuple) else acc
+            if method != "central" and amax > 3:
+                continue  # one-sided stencils of reach > 3: the composition of axis passes (checked below)
+            kw = dict(kw, method=method)
+            x = rng.standard_normal(shape).astype(dtype)
+            with _env(FDX_HESS_ZC=16 if shape[0] == 70 else 0):
+                out = _call("hessian", x, **kw)
+            assert _cabi.last_kernel() == "fused_hessian3d", (shape, kw, _cabi.last_kernel())
+            ref = O.hessian(x, **kw)
+            assert out.shape == ref.shape and out.dtype == ref.dtype
+            err = parity_error("hessian", x, kw, out, ref)
+            assert err <= TOL[np.dtype(dtype)], (shape, kw, err)
+            for i in range(3):
+                for j in range(3):
+                    assert np.array_equal(out[i, j], out[min(i + j, 2), i + j - min(i + j, 2)]), (i, j)
+    # not covered by the fused kernel: still the GPU, as a composition
+    x = rng.standard_normal((30, 30, 30)).astype(dtype)  # last axis not a multiple of the 16-byte vector (fp32)
+    kw = dict(accuracy=8, step_size=0.1)
+    out = _call("hessian", x, **kw)
+    assert _cabi.last_kernel() != "fused_hessian3d"
+    assert parity_error("hessian", x, kw, out, O.hessian(x, **kw)) <= TOL[np.dtype(dtype)]
+
+
+def test_fused_hessian3d_against_the_composition_on_a_big_grid():
+    """Fused one-pass hessian == the 7-pass composition of axis kernels within the parity bound (the nesting order of the
+    mixed entries differs, the boundary rows are the same dense rows), on a grid of several chunks and tiles; inf in the
+    input stays confined to the points whose stencils reach it."""
+    x = torch.randn((96, 160, 256), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    kw = dict(accuracy=4, step_size=(0.1, 0.2, 0.3))
+    h = fdx.hessian(x, **kw)
+    assert _cabi.last_kernel() == "fused_hessian3d"
+    with _env(FDX_HESS_DISABLE=1):
+        h0 = fdx.hessian(x, **kw)
+    assert _cabi.last_kernel() != "fused_hessian3d"
+    sc = h0.abs().amax(dim=(2, 3, 4), keepdim=True)
+    assert ((h - h0).abs() / sc).max().item() <= 2e-5
+    xi = x.clone()
+    xi[50, 80, 128] = float("inf")
+    hi, hi0 = fdx.hessian(xi, **kw), None
+    with _env(FDX_HESS_DISABLE=1):
+        hi0 = fdx.hessian(xi, **kw)
+    assert torch.equal(torch.isfinite(hi), torch.isfinite(hi0))
 
 
 def test_big_array_kernels_inside_a_cuda_graph_capture():
