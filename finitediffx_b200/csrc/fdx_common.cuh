@@ -14,6 +14,7 @@ struct fdx_plan_s {
   double main_taps[FDX_MAX_TAPS];
   double* band_l;  // device, nl*wl
   double* band_r;  // device, nr*wr
+  double* d_main;  // device copy of main_taps (kernels that index the taps at run time: an indexed constant-bank load is slow)
   double* h_band_l;  // host copies (the fused kernels carry the bands in their parameter block)
   double* h_band_r;
   int device;

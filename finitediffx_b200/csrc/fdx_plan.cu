@@ -100,9 +100,11 @@ extern "C" int fdx_plan_create(fdx_plan_t* plan, const fdx_axis_desc* d) {
   p->n = d->n, p->lo = d->lo, p->hi = d->hi;
   p->nl = d->nl, p->wl = d->wl, p->nr = d->nr, p->wr = d->wr;
   std::memcpy(p->main_taps, d->main_taps, sizeof(p->main_taps));
-  p->band_l = p->band_r = nullptr;
+  p->band_l = p->band_r = p->d_main = nullptr;
   p->h_band_l = p->h_band_r = nullptr;
   cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_main, sizeof(p->main_taps));
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_main, p->main_taps, sizeof(p->main_taps), cudaMemcpyHostToDevice);
   const size_t bl = sizeof(double) * (size_t)d->nl * d->wl, br = sizeof(double) * (size_t)d->nr * d->wr;
   if (e == cudaSuccess && bl) e = cudaMalloc((void**)&p->band_l, bl);
   if (e == cudaSuccess && bl) e = cudaMemcpy(p->band_l, d->band_l, bl, cudaMemcpyHostToDevice);
@@ -122,6 +124,7 @@ extern "C" int fdx_plan_create(fdx_plan_t* plan, const fdx_axis_desc* d) {
   if (e != cudaSuccess) {
     cudaFree(p->band_l);
     cudaFree(p->band_r);
+    cudaFree(p->d_main);
     delete[] p->h_band_l;
     delete[] p->h_band_r;
     delete p;
@@ -136,6 +139,7 @@ extern "C" int fdx_plan_destroy(fdx_plan_t plan) {
   fdx::g_epoch.fetch_add(1, std::memory_order_acq_rel);
   cudaFree(plan->band_l);
   cudaFree(plan->band_r);
+  cudaFree(plan->d_main);
   delete[] plan->h_band_l;
   delete[] plan->h_band_r;
   delete plan;
