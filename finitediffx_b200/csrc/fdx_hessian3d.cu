@@ -56,6 +56,7 @@ struct XBand {
 };
 constexpr int kXBandMax = 4;  // band columns per side the march handles (reach of the second derivative <= 4)
 constexpr int kXBandW = 12;   // taps per band row (first-derivative reach <= 3: wl <= 4 + 7)
+constexpr int kYBandMax = 3;  // band rows of axis 1 per side (first-derivative reach <= 3)
 
 // One band element: kXBandW taps from the CTA's table in shared memory (scaled, zero-padded) over a staged row; `row`
 // points at the staged element under the band's first column, `w` is the band's width (lanes past it re-read its last
@@ -87,6 +88,7 @@ struct HessParams {
   // boundary rows of the last axis (dense bands of the first- / second-derivative plan, unscaled float64 in device memory):
   // evaluated by the march itself from its staged rows, a lane per band column
   XBand xb1, xb2;
+  XBand yb;  // boundary rows of axis 1 (first derivative): a warp whose row is a band row runs the dense row instead
 };
 
 // ---- boundary shell -------------------------------------------------------------------------------------------------
@@ -238,6 +240,7 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
   __shared__ __align__(16) T gs[G::GS_ELEMS];
   __shared__ T bt[4][kXBandMax][kXBandW];     // band rows of the last axis: {D_2 left, D_2 right, D2_2 left, D2_2 right}
   __shared__ T d22b[G::TY][2 * kXBandMax];    // D2_2 x on the band columns of the tile rows (left | right)
+  __shared__ T ybt[2][kYBandMax][kXBandW];    // band rows of axis 1 (top | bottom), scaled
 
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   int b = blockIdx.x;
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
   const int zc0 = prm.z_lo + b * prm.zc, zc1 = min(zc0 + prm.zc, prm.z_hi);
   // (the last tile of a row is anchored at the end of the row: it overlaps its neighbour -- the same values are stored
   // twice -- and always holds the columns under the right band rows)
-  const int x0 = min(tx * TX, max(0, prm.n2 - TX)), y0 = ty * G::TY;
+  const int x0 = min(tx * TX, max(0, prm.n2 - TX)), y0 = min(ty * G::TY, max(0, prm.n1 - G::TY));
   const bool edge_l = x0 == 0 && (prm.xb1.nl > 0 || prm.xb2.nl > 0), edge_r = x0 + TX >= prm.n2 && (prm.xb1.nr > 0 || prm.xb2.nr > 0);
   if ((edge_l | edge_r) && tid < 4 * kXBandMax * kXBandW) {
     const int t = tid / (kXBandMax * kXBandW), j = (tid / kXBandW) % kXBandMax, c = tid % kXBandW;
@@ -257,6 +260,13 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
     const int rows = left ? xb.nl : xb.nr, w = left ? xb.wl : xb.wr;
     const double* tab = left ? xb.l : xb.r;
     bt[t][j][c] = (j < rows && c < w) ? (T)(tab[j * w + c] * xb.alpha) : (T)0;  // (visible after the loop's first barrier)
+  }
+  const bool edge_t = y0 < prm.yb.nl, edge_b = y0 + G::TY > prm.n1 - prm.yb.nr;
+  if ((edge_t | edge_b) && tid < 2 * kYBandMax * kXBandW) {
+    const int u = tid, t = u / (kYBandMax * kXBandW), j = (u / kXBandW) % kYBandMax, c = u % kXBandW;
+    const int rows = t == 0 ? prm.yb.nl : prm.yb.nr, w = t == 0 ? prm.yb.wl : prm.yb.wr;
+    const double* tab = t == 0 ? prm.yb.l : prm.yb.r;
+    ybt[t][j][c] = (j < rows && c < w) ? (T)(tab[j * w + c] * prm.yb.alpha) : (T)0;
   }
   // helper work of an edge tile, done by warps 4..7 in stage B (warps 0..3 have a second row there): D_2 x on the band
   // columns of every staged row -> gs, D2_2 x on the band columns of the tile rows -> d22b
@@ -299,7 +309,12 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
 
   // own vector
   const int yo = y0 + wrp, xo = x0 + lane * V;
-  const bool own = yo >= prm.y_lo && yo < prm.y_hi && xo >= prm.x_lo && xo < prm.x_hi;  // (the rest belongs to the shell CTAs)
+  const bool own = yo >= prm.y_lo && yo < prm.y_hi && xo >= prm.x_lo && xo < prm.x_hi;
+  // a warp whose row is a boundary row of axis 1: band table (0 top, 1 bottom), row in it, staged row under its first column
+  const int ybk = yo < prm.yb.nl ? 0 : (yo >= prm.n1 - prm.yb.nr && yo < prm.n1 ? 1 : -1);
+  const int ybj = ybk == 0 ? yo : yo - (prm.n1 - prm.yb.nr);
+  const int ybw = ybk == 0 ? prm.yb.wl : prm.yb.wr;
+  const int ybr = (ybk == 0 ? 0 : prm.n1 - prm.yb.wr) - y0 + P1;
   const int64_t ooff = (int64_t)yo * prm.n2 + xo;
 
   T q0[2 * P2][V], q1[2 * P1][V], q2[2 * P1][V];
@@ -408,6 +423,22 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
           if ((bm2 >> p) & 1) d22.v[p] = col < prm.xb2.nl && edge_l ? d22b[wrp][col] : d22b[wrp][kXBandMax + col - (prm.n2 - prm.xb2.nr)];
         }
       }
+      if (ybk >= 0) {  // (warp-uniform) dense boundary row of axis 1 over the staged rows; zero taps skipped
+        const VecT gc = *reinterpret_cast<const VecT*>(&gs[(wrp + P1) * TX + lane * V]);
+#pragma unroll
+        for (int p = 0; p < V; ++p) gxc[p] = gc.v[p];
+        for (int c = 0; c < ybw; ++c) {
+          const T k = ybt[ybk][ybj][c];
+          if (k == (T)0) continue;
+          const VecT gj = *reinterpret_cast<const VecT*>(&gs[(ybr + c) * TX + lane * V]);
+          const VecT xj = *reinterpret_cast<const VecT*>(&X[((ybr + c) * XSV + lane + HXV) * V]);
+#pragma unroll
+          for (int p = 0; p < V; ++p) {
+            gyv[p] = fma(k, xj.v[p], gyv[p]);
+            d12.v[p] = fma(k, gj.v[p], d12.v[p]);
+          }
+        }
+      } else
 #pragma unroll
       for (int j = 0; j < W1; ++j) {
         const VecT gj = *reinterpret_cast<const VecT*>(&gs[(wrp + j) * TX + lane * V]);
@@ -495,6 +526,7 @@ int launch_hess(const fdx_plan_s* const d1[3], const fdx_plan_s* d2z, const fdx_
   prm.plain_stores = env_int("FDX_HESS_PLAIN_ST", 0);
   prm.xb1 = XBand{d1[2]->band_l, d1[2]->band_r, d1[2]->nl, d1[2]->wl, d1[2]->nr, d1[2]->wr, a1[2]};
   prm.xb2 = XBand{d2x->band_l, d2x->band_r, d2x->nl, d2x->wl, d2x->nr, d2x->wr, a2x};
+  prm.yb = XBand{d1[1]->band_l, d1[1]->band_r, d1[1]->nl, d1[1]->wl, d1[1]->nr, d1[1]->wr, a1[1]};
   fill_taps<T, P1 + 1>(prm.c2z, d2z, a2z);
   fill_taps<T, P1 + 1>(prm.c2x, d2x, a2x);
   fill_taps<T, P1>(prm.c1z, d1[0], a1[0]);
@@ -570,7 +602,10 @@ int run_hess(const fdx_plan_t d1_in[3], const fdx_plan_t d2_in[3], const T* x, T
   ShellParams<T> sh;
   sh.x = x, sh.h = h, sh.n0 = n0, sh.n1 = n1, sh.n2 = n2;
   sh.bz0 = std::max(d1[0]->nl, d2z->nl), sh.bz1 = n0 - std::max(d1[0]->nr, d2z->nr);
-  sh.by0 = d1[1]->nl, sh.by1 = n1 - d1[1]->nr;
+  // (rows: the march runs the band rows of axis 1 itself, a warp per row; its last tile is anchored at the end of the axis
+  // so that the staged rows hold every row under the bottom band)
+  sh.by0 = 0, sh.by1 = n1;
+  if (d1[1]->nl > kYBandMax || d1[1]->nr > kYBandMax || d1[1]->wl > kXBandW || d1[1]->wr > kXBandW) return FDX_EUNSUPPORTED;
   // (columns: the march evaluates the band rows of the last axis itself -- a sector written half by the march and half by
   // the shell is two partial writes (+50 % on the fp32 march), a shell of whole sectors is 16 columns per row)
   sh.bx0 = 0, sh.bx1 = n2;
