@@ -7,18 +7,25 @@
 // and H[i][j] = F[i + j] (:524-529).  This kernel produces exactly those five fields and stores each of them in every
 // slot (i, j) with i + j = key of the (3, 3, n0, n1, n2) result.
 //
-// Two launches (disjoint output points):
-//   the march          the points whose rows are main rows on all three axes.  There the nested differences are pure
-//                      tensor products of the main stencils (operators on different axes commute), so a CTA marches a
-//                      (8 x 32 vectors) tile along axis 0: plane z is staged in shared memory (cp.async, zero fill outside
-//                      the grid, a ring of four planes), a first stage writes gx = D_2 x of the tile and its y halo rows to
-//                      shared memory, the second stage gives every thread D2_2 x, gy = D_1 x and D_1 gx of its vector, and
-//                      three shift-register queues along z (x -> D2_0 x, gy -> D_0 D_1 x, gx -> D_0 D_2 x) complete
-//                      planes z - P2 / z - P1.  All taps sit in the parameter block pre-multiplied by the scales.
-//   the shell          the boundary shell (points in a band row of any axis: the reference's one-sided rows,
-//                      finite_diff.py:75-88; along the last axis rounded to whole vectors): nested dense gathers with
-//                      the plans' band tables, accumulated in float64 (a kernel of its own: 64 registers, full
-//                      occupancy for its latency-bound gathers; as leading CTAs of the march it ran 5x slower).
+// ONE launch.  Operators on different axes commute, so the nested differences are tensor products of the 1-D rows
+// (main stencil or dense boundary row, finite_diff.py:75-88) -- which is what lets a single march produce them:
+//   chunks of the march  a CTA marches a (8 rows x 32 vectors) tile along axis 0 over the planes whose rows of axis 0 are
+//                        main rows: plane z is staged in shared memory (cp.async, zero fill outside the grid, a ring of
+//                        four planes); stage B writes gx = D_2 x of the tile rows and their y halo to shared memory;
+//                        stage C gives every thread D2_2 x, gy = D_1 x and D_1 gx of its vector; three shift-register
+//                        queues along z (x -> D2_0 x, gy -> D_0 D_1 x, gx -> D_0 D_2 x) complete planes z - P2 / z - P1.
+//                        Main taps sit in the parameter block pre-multiplied by the scales.
+//   boundary rows        axis 2: the band columns of gx (all staged rows) and of D2_2 x (tile rows) are evaluated by helper
+//                        lanes of warps 4..7 in stage B (warps 0..3 have a second staged row there) from a scaled
+//                        coefficient table in shared memory, and patched into the owners' vectors; the last tile of a row
+//                        is anchored at the end of the row so that it holds the columns under the right band.
+//                        axis 1: a warp whose row is a band row runs the dense row over the staged rows (warp-uniform).
+//                        axis 0: the band planes get short CTAs of their own behind the chunks: with Gz = (row zb of D_0) x
+//                        -- ONE plane, built in shared memory from the planes under the band -- the mixed entries are
+//                        D_1 Gz and D_2 Gz: stages B and C run once on the Gz tile and once on plane zb itself.
+// (History, measured at 384^3 fp32 accuracy 4: a separate gather kernel over the boundary shell cost 0.28-0.44 ms next to a
+// 0.47 ms march -- nested gathers at ~2000 instructions per point -- and a 32-byte sector written half by the march and half
+// by the shell is two partial writes: +50 % on the march.  All rows in the march: 0.49 ms for everything.)
 #include <algorithm>
 
 #include "fdx_common.cuh"
@@ -47,6 +54,22 @@ struct HessGeom {
   static constexpr int NLD = (ROWS * XSV + NT - 1) / NT;
   static constexpr int NGX = (ROWS * TXV + NT - 1) / NT;
 };
+
+struct AxisTab {
+  const double* bl;
+  const double* br;
+  const double* main;  // device copy of the main taps (an indexed constant-bank load per tap made the shell LDC-bound)
+  int32_t n, lo, hi, nl, wl, nr, wr;
+};
+struct RowOp {
+  const double* c;  // the row's taps (device memory)
+  int32_t s, cnt;
+};
+__device__ __forceinline__ RowOp row_of(const AxisTab& a, int i) {
+  if (i < a.nl) return RowOp{a.bl + (int64_t)i * a.wl, 0, a.wl};
+  if (i >= a.n - a.nr) return RowOp{a.br + (int64_t)(i - (a.n - a.nr)) * a.wr, a.n - a.wr, a.wr};
+  return RowOp{a.main, i + a.lo, a.hi - a.lo + 1};
+}
 
 struct XBand {
   const double* l;
@@ -89,120 +112,13 @@ struct HessParams {
   // evaluated by the march itself from its staged rows, a lane per band column
   XBand xb1, xb2;
   XBand yb;  // boundary rows of axis 1 (first derivative): a warp whose row is a band row runs the dense row instead
+  // boundary planes of axis 0: CTAs of their own behind the chunks of the march (block index / tiles >= n_chunks)
+  AxisTab zt1, zt2;
+  double a1z, a2z;
+  int32_t n_chunks;
 };
 
 // ---- boundary shell -------------------------------------------------------------------------------------------------
-struct AxisTab {
-  const double* bl;
-  const double* br;
-  const double* main;  // device copy of the main taps (an indexed constant-bank load per tap made the shell LDC-bound)
-  int32_t n, lo, hi, nl, wl, nr, wr;
-};
-struct RowOp {
-  const double* c;  // the row's taps (device memory)
-  int32_t s, cnt;
-};
-__device__ __forceinline__ RowOp row_of(const AxisTab& a, int i) {
-  if (i < a.nl) return RowOp{a.bl + (int64_t)i * a.wl, 0, a.wl};
-  if (i >= a.n - a.nr) return RowOp{a.br + (int64_t)(i - (a.n - a.nr)) * a.wr, a.n - a.wr, a.wr};
-  return RowOp{a.main, i + a.lo, a.hi - a.lo + 1};
-}
-__device__ __forceinline__ double tap_of(const AxisTab&, const RowOp& r, int k) { return __ldg(r.c + k); }
-
-// One row of an axis operator applied to a strided line: taps in batches of eight, all loads of a batch issued before
-// the first use (the shell is latency-bound: one load in flight per thread cost 275 us at 384^3, five times the march's
-// share of the work).  Lanes past the row's length re-read its last element with a zero coefficient.
-template <typename T>
-__device__ __forceinline__ double row_dot(const AxisTab& a, const RowOp& r, const T* base, int64_t stride) {
-  double acc = 0;
-  const T* p0 = base + (int64_t)r.s * stride;
-  for (int k0 = 0; k0 < r.cnt; k0 += 8) {
-    double c[8];
-    T v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int k = min(k0 + u, r.cnt - 1);
-      c[u] = k0 + u < r.cnt ? tap_of(a, r, k) : 0.0;
-      v[u] = p0[(int64_t)k * stride];
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc = fma(c[u], c[u] != 0.0 ? (double)v[u] : 0.0, acc);
-  }
-  return acc;
-}
-
-template <typename T>
-struct ShellParams {
-  const T* x;
-  T* h;
-  int32_t n0, n1, n2;
-  int32_t bz0, bz1, by0, by1, bx0, bx1;  // main (band-free) index ranges per axis
-  int64_t cnt_a, cnt_b, cnt_c;
-  double s00, s22, s01, s02, s12;  // scales of the five entries
-  AxisTab d1z, d1y, d1x, d2z, d2x;
-};
-
-template <typename T>
-__device__ __forceinline__ void shell_point(const ShellParams<T>& prm, int64_t idx) {
-  int z, y, x;
-  const int nzb = prm.n0 - (prm.bz1 - prm.bz0), nyb = prm.n1 - (prm.by1 - prm.by0), nxb = prm.n2 - (prm.bx1 - prm.bx0);
-  if (idx < prm.cnt_a) {  // band planes of axis 0, whole planes
-    const int64_t pl = (int64_t)prm.n1 * prm.n2;
-    const int zi = (int)(idx / pl);
-    const int64_t rem = idx - (int64_t)zi * pl;
-    z = zi < prm.bz0 ? zi : prm.bz1 + (zi - prm.bz0);
-    y = (int)(rem / prm.n2), x = (int)(rem - (int64_t)y * prm.n2);
-    (void)nzb;
-  } else if (idx < prm.cnt_a + prm.cnt_b) {  // main planes, band rows of axis 1
-    idx -= prm.cnt_a;
-    const int64_t pl = (int64_t)nyb * prm.n2;
-    const int zi = (int)(idx / pl);
-    const int64_t rem = idx - (int64_t)zi * pl;
-    const int yi = (int)(rem / prm.n2);
-    z = prm.bz0 + zi;
-    y = yi < prm.by0 ? yi : prm.by1 + (yi - prm.by0);
-    x = (int)(rem - (int64_t)yi * prm.n2);
-  } else if (idx < prm.cnt_a + prm.cnt_b + prm.cnt_c) {  // main planes and rows, band columns of axis 2
-    idx -= prm.cnt_a + prm.cnt_b;
-    const int64_t pl = (int64_t)(prm.by1 - prm.by0) * nxb;
-    const int zi = (int)(idx / pl);
-    const int64_t rem = idx - (int64_t)zi * pl;
-    const int yi = (int)(rem / nxb), xi = (int)(rem - (int64_t)yi * nxb);
-    z = prm.bz0 + zi, y = prm.by0 + yi;
-    x = xi < prm.bx0 ? xi : prm.bx1 + (xi - prm.bx0);
-  } else {
-    return;
-  }
-  const int64_t s1 = prm.n2, s0 = (int64_t)prm.n1 * prm.n2, N = s0 * prm.n0;
-  const T* X = prm.x;
-  const int64_t at = (int64_t)z * s0 + (int64_t)y * s1 + x;
-
-  const RowOp rz = row_of(prm.d1z, z), ry = row_of(prm.d1y, y), rx = row_of(prm.d1x, x);
-  const RowOp rz2 = row_of(prm.d2z, z), rx2 = row_of(prm.d2x, x);
-  const double d00 = row_dot<T>(prm.d2z, rz2, X + (int64_t)y * s1 + x, s0);
-  const double d22 = row_dot<T>(prm.d2x, rx2, X + (int64_t)z * s0 + (int64_t)y * s1, 1);
-  double d01 = 0, d02 = 0, d12 = 0;
-  for (int k = 0; k < rz.cnt; ++k) {
-    const double cz = tap_of(prm.d1z, rz, k);
-    if (cz == 0.0) continue;  // (zero taps never touch their data: 0 * inf stays out, as in the axis kernels' band rows)
-    const T* pz = X + (int64_t)(rz.s + k) * s0;
-    d01 = fma(cz, row_dot<T>(prm.d1y, ry, pz + x, s1), d01);
-    d02 = fma(cz, row_dot<T>(prm.d1x, rx, pz + (int64_t)y * s1, 1), d02);
-  }
-  for (int j = 0; j < ry.cnt; ++j) {
-    const double cy = tap_of(prm.d1y, ry, j);
-    if (cy == 0.0) continue;
-    d12 = fma(cy, row_dot<T>(prm.d1x, rx, X + (int64_t)z * s0 + (int64_t)(ry.s + j) * s1, 1), d12);
-  }
-  T* o = prm.h + at;
-  const T v0 = (T)(d00 * prm.s00), v1 = (T)(d01 * prm.s01), v2 = (T)(d02 * prm.s02), v3 = (T)(d12 * prm.s12), v4 = (T)(d22 * prm.s22);
-  o[0] = v0;
-  o[1 * N] = v1, o[3 * N] = v1;
-  o[2 * N] = v2, o[4 * N] = v2, o[6 * N] = v2;
-  o[5 * N] = v3, o[7 * N] = v3;
-  o[8 * N] = v4;
-}
-
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   const int sz = valid ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled, nothing is read
@@ -223,11 +139,6 @@ __device__ __forceinline__ void st_cs(T* p, const Vec<T, V>& r, bool plain = fal
   } else {
     __stcs(reinterpret_cast<double2*>(p), make_double2(r.v[0], r.v[1]));
   }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(128) hessian3d_shell(const __grid_constant__ ShellParams<T> prm) {
-  shell_point<T>(prm, (int64_t)blockIdx.x * 128 + threadIdx.x);
 }
 
 template <typename T, int P1, int MINB>
@@ -317,35 +228,9 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
   const int ybr = (ybk == 0 ? 0 : prm.n1 - prm.yb.wr) - y0 + P1;
   const int64_t ooff = (int64_t)yo * prm.n2 + xo;
 
-  T q0[2 * P2][V], q1[2 * P1][V], q2[2 * P1][V];
-#pragma unroll
-  for (int j = 0; j < 2 * P2; ++j)
-#pragma unroll
-    for (int p = 0; p < V; ++p) q0[j][p] = (T)0;
-#pragma unroll
-  for (int j = 0; j < 2 * P1; ++j)
-#pragma unroll
-    for (int p = 0; p < V; ++p) q1[j][p] = q2[j][p] = (T)0;
-
-  const int zfirst = zc0 - P2, zlast = zc1 - 1 + P2;
-#pragma unroll
-  for (int s = 0; s < NS - 1; ++s) {  // (one group per plane, empty groups past the end keep the count uniform)
-    if (zfirst + s <= zlast) stage(zfirst + s, s);
-    cp_async_commit();
-  }
-  int cur = 0;
-  for (int z = zfirst; z <= zlast; ++z) {
-    cp_async_wait<NS - 2>();  // plane z has landed
-    __syncthreads();          // ... for every thread; and the buffer of plane z - 1 is free
-    {
-      const int nb = cur == 0 ? NS - 1 : cur - 1;
-      if (z + NS - 1 <= zlast) stage(z + NS - 1, nb);
-      cp_async_commit();
-    }
-    const T* X = xs[cur];
-    cur = cur + 1 == NS ? 0 : cur + 1;
-
-    // ---- stage B: gx = D_2 x on the tile rows and their y halo
+  // ---- stage B: gx = D_2 x on the staged rows (tile rows and their y halo) -> gs; edge tiles: the band columns of it and
+  // of D2_2 x by the helper lanes
+  auto stage_b = [&](const T* X) {
 #pragma unroll
     for (int s = 0; s < G::NGX; ++s) {
       const int r = wrp + s * 8;
@@ -391,12 +276,9 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
           gs[r * TX + (right ? prm.n2 - nb + j : j) - x0] = v;
       }
     }
-    __syncthreads();
-
-    // ---- stage C: the thread's own vector of plane z
-    const bool inplane = z >= zc0 && z < zc1;
-    T xc[V], gyv[V], gxc[V];
-    {
+  };
+  // ---- stage C: the thread's own vector of the staged plane: its value, D2_2 x, gy = D_1 x, gx = D_2 x and D_1 gx
+  auto stage_c = [&](const T* X, T (&xc)[V], T (&gyv)[V], T (&gxc)[V], VecT& d22, VecT& d12) {
       T w[G::WV * V];
       const int r = wrp + P1;
 #pragma unroll
@@ -407,7 +289,6 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
       }
 #pragma unroll
       for (int p = 0; p < V; ++p) xc[p] = w[HX + p];
-      VecT d22, d12;
 #pragma unroll
       for (int p = 0; p < V; ++p) {
         T a = (T)0;
@@ -455,6 +336,107 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
           d12.v[p] = fma(prm.c1y[j], gj.v[p], d12.v[p]);
         }
       }
+  };
+  if (b >= prm.n_chunks) {
+    // ---- a boundary plane of axis 0 (the dense rows of both plans there): no queue.  With Gz = (row zb of D_0) x, a single
+    // plane, the mixed entries are D_1 Gz and D_2 Gz -- the in-plane stages run on the staged Gz tile and on plane zb itself
+    const int zi = b - prm.n_chunks;
+    const int zb = zi < prm.z_lo ? zi : prm.z_hi + (zi - prm.z_lo);
+    stage(zb, 1);
+    cp_async_commit();
+    const RowOp r1 = row_of(prm.zt1, zb), r2 = row_of(prm.zt2, zb);
+#pragma unroll
+    for (int s = 0; s < G::NLD; ++s)
+      if (soff[s] >= 0) {
+        VecT acc;
+#pragma unroll
+        for (int p = 0; p < V; ++p) acc.v[p] = (T)0;
+        if (ok[s])
+          for (int c = 0; c < r1.cnt; ++c) {
+            const T k = (T)(__ldg(r1.c + c) * prm.a1z);
+            if (k == (T)0) continue;
+            const VecT v = ld_cached<T, V>(prm.x + (int64_t)(r1.s + c) * plane + goff[s]);
+#pragma unroll
+            for (int p = 0; p < V; ++p) acc.v[p] = fma(k, v.v[p], acc.v[p]);
+          }
+        *reinterpret_cast<VecT*>(&xs[0][soff[s]]) = acc;
+      }
+    VecT d00;
+#pragma unroll
+    for (int p = 0; p < V; ++p) d00.v[p] = (T)0;
+    if (own)
+      for (int c = 0; c < r2.cnt; ++c) {
+        const T k = (T)(__ldg(r2.c + c) * prm.a2z);
+        if (k == (T)0) continue;
+        const VecT v = ld_cached<T, V>(prm.x + (int64_t)(r2.s + c) * plane + ooff);
+#pragma unroll
+        for (int p = 0; p < V; ++p) d00.v[p] = fma(k, v.v[p], d00.v[p]);
+      }
+    cp_async_wait<0>();
+    __syncthreads();
+    T xc[V], gyv[V], gxc[V];
+    VecT d22, d12, d01, d02;
+    stage_b(xs[0]);
+    __syncthreads();
+    stage_c(xs[0], xc, gyv, gxc, d22, d12);
+#pragma unroll
+    for (int p = 0; p < V; ++p) d01.v[p] = gyv[p], d02.v[p] = gxc[p];
+    __syncthreads();
+    stage_b(xs[1]);
+    __syncthreads();
+    stage_c(xs[1], xc, gyv, gxc, d22, d12);
+    if (own) {
+      T* o = prm.h + (int64_t)zb * plane + ooff;
+      st_cs<T, V>(o, d00, plain);
+      st_cs<T, V>(o + 1 * N, d01, plain);
+      st_cs<T, V>(o + 3 * N, d01, plain);
+      st_cs<T, V>(o + 2 * N, d02, plain);
+      st_cs<T, V>(o + 4 * N, d02, plain);
+      st_cs<T, V>(o + 6 * N, d02, plain);
+      st_cs<T, V>(o + 5 * N, d12, plain);
+      st_cs<T, V>(o + 7 * N, d12, plain);
+      st_cs<T, V>(o + 8 * N, d22, plain);
+    }
+    return;
+  }
+
+  T q0[2 * P2][V], q1[2 * P1][V], q2[2 * P1][V];
+#pragma unroll
+  for (int j = 0; j < 2 * P2; ++j)
+#pragma unroll
+    for (int p = 0; p < V; ++p) q0[j][p] = (T)0;
+#pragma unroll
+  for (int j = 0; j < 2 * P1; ++j)
+#pragma unroll
+    for (int p = 0; p < V; ++p) q1[j][p] = q2[j][p] = (T)0;
+
+  const int zfirst = zc0 - P2, zlast = zc1 - 1 + P2;
+#pragma unroll
+  for (int s = 0; s < NS - 1; ++s) {  // (one group per plane, empty groups past the end keep the count uniform)
+    if (zfirst + s <= zlast) stage(zfirst + s, s);
+    cp_async_commit();
+  }
+  int cur = 0;
+  for (int z = zfirst; z <= zlast; ++z) {
+    cp_async_wait<NS - 2>();  // plane z has landed
+    __syncthreads();          // ... for every thread; and the buffer of plane z - 1 is free
+    {
+      const int nb = cur == 0 ? NS - 1 : cur - 1;
+      if (z + NS - 1 <= zlast) stage(z + NS - 1, nb);
+      cp_async_commit();
+    }
+    const T* X = xs[cur];
+    cur = cur + 1 == NS ? 0 : cur + 1;
+
+    stage_b(X);
+    __syncthreads();
+
+    // the thread's own vector of plane z
+    const bool inplane = z >= zc0 && z < zc1;
+    T xc[V], gyv[V], gxc[V];
+    {
+      VecT d22, d12;
+      stage_c(X, xc, gyv, gxc, d22, d12);
       if (inplane && own) {
         T* o = prm.h + (int64_t)z * plane + ooff;
         st_cs<T, V>(o + 8 * N, d22, plain);  // key 4: (2,2)
@@ -517,59 +499,54 @@ void fill_taps(T (&c)[2 * P + 1], const fdx_plan_s* p, double scale) {  // (P: t
 
 template <typename T, int P1>
 int launch_hess(const fdx_plan_s* const d1[3], const fdx_plan_s* d2z, const fdx_plan_s* d2x, const T* x, T* h, const double a1[3],
-                double a2z, double a2x, const ShellParams<T>& sh, cudaStream_t st) {
+                double a2z, double a2x, int bz0, int bz1, cudaStream_t st) {
   using G = HessGeom<T, P1>;
   HessParams<T, P1> prm;
   prm.x = x, prm.h = h;
-  prm.n0 = sh.n0, prm.n1 = sh.n1, prm.n2 = sh.n2;
-  prm.z_lo = sh.bz0, prm.z_hi = sh.bz1;
+  prm.n0 = d1[0]->n, prm.n1 = d1[1]->n, prm.n2 = d1[2]->n;
+  prm.z_lo = bz0, prm.z_hi = bz1;
   prm.plain_stores = env_int("FDX_HESS_PLAIN_ST", 0);
   prm.xb1 = XBand{d1[2]->band_l, d1[2]->band_r, d1[2]->nl, d1[2]->wl, d1[2]->nr, d1[2]->wr, a1[2]};
   prm.xb2 = XBand{d2x->band_l, d2x->band_r, d2x->nl, d2x->wl, d2x->nr, d2x->wr, a2x};
   prm.yb = XBand{d1[1]->band_l, d1[1]->band_r, d1[1]->nl, d1[1]->wl, d1[1]->nr, d1[1]->wr, a1[1]};
+  prm.zt1 = tab_of(d1[0]), prm.zt2 = tab_of(d2z), prm.a1z = a1[0], prm.a2z = a2z;
   fill_taps<T, P1 + 1>(prm.c2z, d2z, a2z);
   fill_taps<T, P1 + 1>(prm.c2x, d2x, a2x);
   fill_taps<T, P1>(prm.c1z, d1[0], a1[0]);
   fill_taps<T, P1>(prm.c1y, d1[1], a1[1]);
   fill_taps<T, P1>(prm.c1x, d1[2], a1[2]);
-  prm.y_lo = sh.by0, prm.y_hi = sh.by1, prm.x_lo = sh.bx0, prm.x_hi = sh.bx1;
-  prm.tiles_x = (sh.n2 + G::TX - 1) / G::TX, prm.tiles_y = (sh.n1 + G::TY - 1) / G::TY;
-  prm.zc = 1;
-  const int nz = sh.bz1 - sh.bz0;
-  const int part = env_int("FDX_HESS_PART", 0);  // timing tools: 1 = the march alone, 2 = the shell alone
-  int64_t main_blocks = 0;
-  if (sh.by1 > sh.by0 && sh.bx1 > sh.bx0 && nz > 0 && part != 2) {
-    const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
-    // z chunks of ~64 planes (a chunk re-reads 2 P2 planes), shorter when that leaves fewer than ~3 CTAs per SM
+  prm.y_lo = 0, prm.y_hi = prm.n1, prm.x_lo = 0, prm.x_hi = prm.n2;
+  prm.tiles_x = (prm.n2 + G::TX - 1) / G::TX, prm.tiles_y = (prm.n1 + G::TY - 1) / G::TY;
+  prm.zc = 1, prm.n_chunks = 0;
+  const int nz = bz1 - bz0;
+  const int part = env_int("FDX_HESS_PART", 0);  // timing tools: 1 = the chunks of the march alone, 2 = the z-band planes alone
+  const int64_t tiles = (int64_t)prm.tiles_x * prm.tiles_y;
+  if (nz > 0 && part != 2) {
+    // z chunks of ~32 planes (a chunk re-reads 2 P2 planes; 384^3: 32 beats 48 / 64 / 96 by 1-6 %), shorter when that
+    // leaves fewer than ~3 CTAs per SM
     int zc = env_int("FDX_HESS_ZC", 0);
     if (zc <= 0) {
       const int64_t want = (int64_t)env_int("FDX_HESS_CPS", 3) * num_sms();
-      const int64_t chunks = std::max<int64_t>((nz + 63) / 64, (want + tiles - 1) / tiles);
+      const int64_t chunks = std::max<int64_t>((nz + 31) / 32, (want + tiles - 1) / tiles);
       zc = std::max((int)((nz + chunks - 1) / chunks), 16);
     }
     zc = std::min(zc, nz);
     prm.zc = zc;
-    main_blocks = tiles * ((nz + zc - 1) / zc);
+    prm.n_chunks = (nz + zc - 1) / zc;
   }
-  const int64_t pts = part == 1 ? 0 : sh.cnt_a + sh.cnt_b + sh.cnt_c;
-  const int64_t shell_blocks = (pts + 127) / 128;
-  if (main_blocks + shell_blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
-  if (main_blocks + shell_blocks == 0) return FDX_OK;
-  if (shell_blocks) {
-    hessian3d_shell<T><<<(unsigned)shell_blocks, 128, 0, st>>>(sh);
-    count_launch("fused_hessian3d");
-    FDX_LAUNCH_CHECK();
+  // the boundary planes of axis 0: one short CTA per tile and plane, behind the chunks (they fill the tail of the launch)
+  const int64_t zband_planes = part == 1 ? 0 : prm.n0 - nz;
+  const int64_t blocks = tiles * (prm.n_chunks + zband_planes);
+  if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
+  if (blocks == 0) return FDX_OK;
+  bool three = false;
+  if constexpr (P1 == 2) three = env_int("FDX_HESS_MINB", 2) == 3;
+  if constexpr (P1 == 2) {
+    if (three) hessian3d_kernel<T, P1, 3><<<(unsigned)blocks, G::NT, 0, st>>>(prm);
   }
-  if (main_blocks) {
-    bool three = false;
-    if constexpr (P1 == 2) three = env_int("FDX_HESS_MINB", 2) == 3;
-    if constexpr (P1 == 2) {
-      if (three) hessian3d_kernel<T, P1, 3><<<(unsigned)main_blocks, G::NT, 0, st>>>(prm);
-    }
-    if (!three) hessian3d_kernel<T, P1, (P1 <= 1 ? 3 : 2)><<<(unsigned)main_blocks, G::NT, 0, st>>>(prm);
-    count_launch("fused_hessian3d");
-    FDX_LAUNCH_CHECK();
-  }
+  if (!three) hessian3d_kernel<T, P1, (P1 <= 1 ? 3 : 2)><<<(unsigned)blocks, G::NT, 0, st>>>(prm);
+  count_launch("fused_hessian3d");
+  FDX_LAUNCH_CHECK();
   return FDX_OK;
 }
 
@@ -599,31 +576,20 @@ int run_hess(const fdx_plan_t d1_in[3], const fdx_plan_t d2_in[3], const T* x, T
   if ((int64_t)n1 * n2 >= 0x7fffffffLL) return FDX_EUNSUPPORTED;
   if (((int64_t)n0 * n1 * n2) % V != 0) return FDX_EUNSUPPORTED;
 
-  ShellParams<T> sh;
-  sh.x = x, sh.h = h, sh.n0 = n0, sh.n1 = n1, sh.n2 = n2;
-  sh.bz0 = std::max(d1[0]->nl, d2z->nl), sh.bz1 = n0 - std::max(d1[0]->nr, d2z->nr);
-  // (rows: the march runs the band rows of axis 1 itself, a warp per row; its last tile is anchored at the end of the axis
-  // so that the staged rows hold every row under the bottom band)
-  sh.by0 = 0, sh.by1 = n1;
+  // main rows of axis 0: the chunks of the march; the band planes on either side get CTAs of their own.  The band rows of
+  // axes 1 and 2 are evaluated inside the march (a warp per band row, helper lanes per band column): a separate pass over
+  // the boundary shell cost more than the march itself (nested gathers), and a 32-byte sector written half by each pass is
+  // two partial writes
+  int bz0 = std::max(d1[0]->nl, d2z->nl), bz1 = n0 - std::max(d1[0]->nr, d2z->nr);
+  if (bz1 < bz0) bz1 = bz0;
   if (d1[1]->nl > kYBandMax || d1[1]->nr > kYBandMax || d1[1]->wl > kXBandW || d1[1]->wr > kXBandW) return FDX_EUNSUPPORTED;
-  // (columns: the march evaluates the band rows of the last axis itself -- a sector written half by the march and half by
-  // the shell is two partial writes (+50 % on the fp32 march), a shell of whole sectors is 16 columns per row)
-  sh.bx0 = 0, sh.bx1 = n2;
   if (std::max(d1[2]->nl, d2x->nl) > kXBandMax || std::max(d1[2]->nr, d2x->nr) > kXBandMax) return FDX_EUNSUPPORTED;
-  if (sh.bz1 < sh.bz0) sh.bz1 = sh.bz0;
-  if (sh.by1 < sh.by0) sh.by1 = sh.by0;
-  if (sh.bx1 < sh.bx0) sh.bx1 = sh.bx0;
-  const int64_t mz = sh.bz1 - sh.bz0, my = sh.by1 - sh.by0, mx = sh.bx1 - sh.bx0;
-  sh.cnt_a = (int64_t)(n0 - mz) * n1 * n2;
-  sh.cnt_b = mz * (n1 - my) * n2;
-  sh.cnt_c = mz * my * (n2 - mx);
-  sh.s00 = a2[0], sh.s22 = a2[2], sh.s01 = a1[0] * a1[1], sh.s02 = a1[0] * a1[2], sh.s12 = a1[1] * a1[2];
-  sh.d1z = tab_of(d1[0]), sh.d1y = tab_of(d1[1]), sh.d1x = tab_of(d1[2]), sh.d2z = tab_of(d2z), sh.d2x = tab_of(d2x);
+  if (std::max(std::max(d1[2]->wl, d2x->wl), std::max(d1[2]->wr, d2x->wr)) > kXBandW) return FDX_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   switch (P1) {
-    case 1: return launch_hess<T, 1>(d1, d2z, d2x, x, h, a1, a2[0], a2[2], sh, st);
-    case 2: return launch_hess<T, 2>(d1, d2z, d2x, x, h, a1, a2[0], a2[2], sh, st);
-    default: return launch_hess<T, 3>(d1, d2z, d2x, x, h, a1, a2[0], a2[2], sh, st);
+    case 1: return launch_hess<T, 1>(d1, d2z, d2x, x, h, a1, a2[0], a2[2], bz0, bz1, st);
+    case 2: return launch_hess<T, 2>(d1, d2z, d2x, x, h, a1, a2[0], a2[2], bz0, bz1, st);
+    default: return launch_hess<T, 3>(d1, d2z, d2x, x, h, a1, a2[0], a2[2], bz0, bz1, st);
   }
 }
 
