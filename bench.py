@@ -625,8 +625,12 @@ def _extras_single(fdx, _cabi, dev, peak):
     ex["jacobian_3x384_f32_a4"] = _entry(384**3, 4 * (3 + 9), t, peak, _cabi.last_kernel(), note="one fused gradient per component")
     t = timed(lambda v: fdx.hessian(v, accuracy=4, step_size=0.1), [f3[0]], k=10, wu=3)
     ex["hessian_384_f32_a4"] = _entry(384**3, 4 * (1 + 9), t, peak, _cabi.last_kernel(),
-                                      note="7 axis passes + 4 slot copies (the reference's table entries, bug-compatible); frac counts one read + nine writes")
+                                      note="ONE fused launch (fdx_hessian3d: the reference's table entries, bug-compatible, stored in all nine slots); one read + nine writes")
+    x64 = f3[0].double()
     del f3
+    t = timed(lambda v: fdx.hessian(v, accuracy=4, step_size=0.1), [x64], k=10, wu=3)
+    ex["hessian_384_f64_a4"] = _entry(384**3, 8 * (1 + 9), t, peak, _cabi.last_kernel())
+    del x64
     torch.cuda.empty_cache()
     # ---- config 4: divergence / curl on a (3, 1024^3) fp32 field, accuracy 4 (one input: 12.9 GB, far larger than L2)
     for name in ("divergence_1024_f32_a4_strong", "curl_1024_f32_a4_strong"):
