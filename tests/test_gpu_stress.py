@@ -127,3 +127,51 @@ def test_random_shapes_through_the_tma_ring_kernels():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_tma.py"), "200", "11"], capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0 and "0 mismatches" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_fused_hessian3d_random_shapes_against_the_composition():
+    """Random 3-D hessians: the one-pass kernel (fdx_hessian3d: chunks, anchored edge tiles, helper-lane x bands, band-row warps,
+    z-band CTAs) against the composition of axis kernels (itself checked against the oracle), over shapes from a single
+    partial tile to several tiles and chunks, all methods, per-axis accuracies and both dtypes."""
+    import numpy as np
+
+    rnd = np.random.default_rng(2024)
+    fused = 0
+    for case in range(120):
+        dtype = torch.float32 if case % 3 else torch.float64
+        method = ("central", "forward", "backward")[int(rnd.integers(0, 3))]
+        amax = 6 if method == "central" else 3
+        acc = tuple(int(a) for a in rnd.integers(1 if method != "central" else 2, amax + 1, size=3))
+        if rnd.random() < 0.4:
+            acc = acc[0]
+        v = 4 if dtype == torch.float32 else 2
+        lo = 2 * (amax + 2)
+        shape = (int(rnd.integers(lo, 48)), int(rnd.integers(lo, 40)), int(rnd.integers(lo // v + 1, 280 // v)) * v)
+        steps = tuple(float(h) for h in rnd.uniform(0.1, 1.0, size=3))
+        kw = dict(accuracy=acc, step_size=steps, method=method)
+        x = torch.randn(shape, device="cuda", dtype=dtype, generator=torch.Generator(device="cuda").manual_seed(case))
+        zc = int(rnd.choice([0, 0, 16, 24]))
+        os.environ["FDX_HESS_ZC"] = str(zc)
+        _cabi.reload_env()
+        try:
+            try:
+                h = fdx.hessian(x, **kw)
+            except ValueError:
+                continue  # axis too short for this stencil: the reference's own error
+            kern = _cabi.last_kernel()
+            os.environ["FDX_HESS_DISABLE"] = "1"
+            _cabi.reload_env()
+            h0 = fdx.hessian(x, **kw)
+            assert _cabi.last_kernel() != "fused_hessian3d"
+        finally:
+            os.environ.pop("FDX_HESS_DISABLE", None)
+            os.environ.pop("FDX_HESS_ZC", None)
+            _cabi.reload_env()
+        if kern != "fused_hessian3d":
+            continue
+        fused += 1
+        sc = h0.abs().amax(dim=(2, 3, 4), keepdim=True).clamp_min(1e-30)
+        err = ((h - h0).abs() / sc).max().item()
+        assert err <= (3e-5 if dtype == torch.float32 else 1e-11), (case, shape, kw, zc, err)
+    assert fused >= 80, fused
+
