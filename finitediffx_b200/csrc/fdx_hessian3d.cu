@@ -540,11 +540,11 @@ int launch_hess(const fdx_plan_s* const d1[3], const fdx_plan_s* d2z, const fdx_
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   if (blocks == 0) return FDX_OK;
   bool three = false;
-  if constexpr (P1 == 2) three = env_int("FDX_HESS_MINB", 2) == 3;
-  if constexpr (P1 == 2) {
+  if constexpr (P1 <= 2) three = env_int("FDX_HESS_MINB", 2) == 3;
+  if constexpr (P1 <= 2) {
     if (three) hessian3d_kernel<T, P1, 3><<<(unsigned)blocks, G::NT, 0, st>>>(prm);
   }
-  if (!three) hessian3d_kernel<T, P1, (P1 <= 1 ? 3 : 2)><<<(unsigned)blocks, G::NT, 0, st>>>(prm);
+  if (!three) hessian3d_kernel<T, P1, 2><<<(unsigned)blocks, G::NT, 0, st>>>(prm);
   count_launch("fused_hessian3d");
   FDX_LAUNCH_CHECK();
   return FDX_OK;
