@@ -128,6 +128,54 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// acc += c * x, dst = c * x + src, dst = c * x on 16-byte vectors.  fp32: the packed FFMA2 / FMUL2 (fma.rn.f32x2, sm_100+; two
+// independent IEEE fmas, the bits of the scalar form) -- the fp32 march is issue-limited (ncu: 454 instructions per warp and
+// plane at 2 CTAs per SM), the y taps and the three z queues are whole-vector operations.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long p, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+template <typename T, int V, bool PACK = true>
+__device__ __forceinline__ void vfma_to(Vec<T, V>& dst, T c, const Vec<T, V>& x, const Vec<T, V>& src) {
+  if constexpr (sizeof(T) == 4 && PACK) {
+    const unsigned long long cc = pack2(c, c);
+#pragma unroll
+    for (int h = 0; h < V / 2; ++h) {
+      unsigned long long d;
+      asm("fma.rn.f32x2 %0, %1, %2, %3;"
+          : "=l"(d)
+          : "l"(cc), "l"(pack2(x.v[2 * h], x.v[2 * h + 1])), "l"(pack2(src.v[2 * h], src.v[2 * h + 1])));
+      unpack2(d, dst.v[2 * h], dst.v[2 * h + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < V; ++p) dst.v[p] = fma(c, x.v[p], src.v[p]);
+  }
+}
+template <typename T, int V, bool PACK = true>
+__device__ __forceinline__ void vfma(Vec<T, V>& acc, T c, const Vec<T, V>& x) {
+  vfma_to<T, V, PACK>(acc, c, x, acc);
+}
+template <typename T, int V, bool PACK = true>
+__device__ __forceinline__ void vmul(Vec<T, V>& dst, T c, const Vec<T, V>& x) {
+  if constexpr (sizeof(T) == 4 && PACK) {
+    const unsigned long long cc = pack2(c, c);
+#pragma unroll
+    for (int h = 0; h < V / 2; ++h) {
+      unsigned long long d;
+      asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(cc), "l"(pack2(x.v[2 * h], x.v[2 * h + 1])));
+      unpack2(d, dst.v[2 * h], dst.v[2 * h + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < V; ++p) dst.v[p] = c * x.v[p];
+  }
+}
+
 template <typename T, int V>
 __device__ __forceinline__ void st_cs(T* p, const Vec<T, V>& r, bool plain = false) {
   if (plain) {
@@ -146,6 +194,10 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
   using G = HessGeom<T, P1>;
   constexpr int V = G::V, P2 = G::P2, W1 = G::W1, W2 = G::W2, HX = G::HX, HXV = G::HXV, XSV = G::XSV, TX = G::TX;
   using VecT = Vec<T, V>;
+  // packed fp32 arithmetic for the y taps and the z queues -- except at reach 2, which sits at 128 registers: packed (aligned
+  // register pairs for its 56 queue registers) it spills: 384^3 accuracy 4 0.48 -> 0.53 ms (y taps alone packed: 0.61 ms);
+  // reach 3 gains 11 % (0.69 -> 0.61 ms), reach 1 is unchanged
+  constexpr bool PQ = P1 != 2;
   constexpr int NS = G::NS;
   __shared__ __align__(16) T xs[NS][G::XS_ELEMS];
   __shared__ __align__(16) T gs[G::GS_ELEMS];
@@ -278,7 +330,7 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
     }
   };
   // ---- stage C: the thread's own vector of the staged plane: its value, D2_2 x, gy = D_1 x, gx = D_2 x and D_1 gx
-  auto stage_c = [&](const T* X, T (&xc)[V], T (&gyv)[V], T (&gxc)[V], VecT& d22, VecT& d12) {
+  auto stage_c = [&](const T* X, VecT& xc, VecT& gyv, VecT& gxc, VecT& d22, VecT& d12) {
       T w[G::WV * V];
       const int r = wrp + P1;
 #pragma unroll
@@ -288,14 +340,14 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
         for (int p = 0; p < V; ++p) w[u * V + p] = t.v[p];
       }
 #pragma unroll
-      for (int p = 0; p < V; ++p) xc[p] = w[HX + p];
+      for (int p = 0; p < V; ++p) xc.v[p] = w[HX + p];
 #pragma unroll
       for (int p = 0; p < V; ++p) {
         T a = (T)0;
 #pragma unroll
         for (int k = 0; k < W2; ++k) a = fma(prm.c2x[k], w[HX - P2 + p + k], a);
         d22.v[p] = a;
-        gyv[p] = (T)0, d12.v[p] = (T)0;
+        gyv.v[p] = (T)0, d12.v[p] = (T)0;
       }
       if (bm2 != 0) {  // band columns of D2_2 x: from the helper lanes
 #pragma unroll
@@ -305,19 +357,14 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
         }
       }
       if (ybk >= 0) {  // (warp-uniform) dense boundary row of axis 1 over the staged rows; zero taps skipped
-        const VecT gc = *reinterpret_cast<const VecT*>(&gs[(wrp + P1) * TX + lane * V]);
-#pragma unroll
-        for (int p = 0; p < V; ++p) gxc[p] = gc.v[p];
+        gxc = *reinterpret_cast<const VecT*>(&gs[(wrp + P1) * TX + lane * V]);
         for (int c = 0; c < ybw; ++c) {
           const T k = ybt[ybk][ybj][c];
           if (k == (T)0) continue;
           const VecT gj = *reinterpret_cast<const VecT*>(&gs[(ybr + c) * TX + lane * V]);
           const VecT xj = *reinterpret_cast<const VecT*>(&X[((ybr + c) * XSV + lane + HXV) * V]);
-#pragma unroll
-          for (int p = 0; p < V; ++p) {
-            gyv[p] = fma(k, xj.v[p], gyv[p]);
-            d12.v[p] = fma(k, gj.v[p], d12.v[p]);
-          }
+          vfma<T, V, PQ>(gyv, k, xj);
+          vfma<T, V, PQ>(d12, k, gj);
         }
       } else
 #pragma unroll
@@ -325,16 +372,12 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
         const VecT gj = *reinterpret_cast<const VecT*>(&gs[(wrp + j) * TX + lane * V]);
         VecT xj;
         if (j == P1) {
-#pragma unroll
-          for (int p = 0; p < V; ++p) xj.v[p] = xc[p], gxc[p] = gj.v[p];
+          xj = xc, gxc = gj;
         } else {
           xj = *reinterpret_cast<const VecT*>(&X[((wrp + j) * XSV + lane + HXV) * V]);
         }
-#pragma unroll
-        for (int p = 0; p < V; ++p) {
-          gyv[p] = fma(prm.c1y[j], xj.v[p], gyv[p]);
-          d12.v[p] = fma(prm.c1y[j], gj.v[p], d12.v[p]);
-        }
+        vfma<T, V, PQ>(gyv, prm.c1y[j], xj);
+        vfma<T, V, PQ>(d12, prm.c1y[j], gj);
       }
   };
   if (b >= prm.n_chunks) {
@@ -374,13 +417,12 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
       }
     cp_async_wait<0>();
     __syncthreads();
-    T xc[V], gyv[V], gxc[V];
+    VecT xc, gyv, gxc;
     VecT d22, d12, d01, d02;
     stage_b(xs[0]);
     __syncthreads();
     stage_c(xs[0], xc, gyv, gxc, d22, d12);
-#pragma unroll
-    for (int p = 0; p < V; ++p) d01.v[p] = gyv[p], d02.v[p] = gxc[p];
+    d01 = gyv, d02 = gxc;
     __syncthreads();
     stage_b(xs[1]);
     __syncthreads();
@@ -400,15 +442,15 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
     return;
   }
 
-  T q0[2 * P2][V], q1[2 * P1][V], q2[2 * P1][V];
+  VecT q0[2 * P2], q1[2 * P1], q2[2 * P1];
 #pragma unroll
   for (int j = 0; j < 2 * P2; ++j)
 #pragma unroll
-    for (int p = 0; p < V; ++p) q0[j][p] = (T)0;
+    for (int p = 0; p < V; ++p) q0[j].v[p] = (T)0;
 #pragma unroll
   for (int j = 0; j < 2 * P1; ++j)
 #pragma unroll
-    for (int p = 0; p < V; ++p) q1[j][p] = q2[j][p] = (T)0;
+    for (int p = 0; p < V; ++p) q1[j].v[p] = q2[j].v[p] = (T)0;
 
   const int zfirst = zc0 - P2, zlast = zc1 - 1 + P2;
 #pragma unroll
@@ -433,7 +475,7 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
 
     // the thread's own vector of plane z
     const bool inplane = z >= zc0 && z < zc1;
-    T xc[V], gyv[V], gxc[V];
+    VecT xc, gyv, gxc;
     {
       VecT d22, d12;
       stage_c(X, xc, gyv, gxc, d22, d12);
@@ -446,29 +488,19 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
     }
     // ---- z queues: plane z completes D2_0 x of plane z - P2 and the mixed entries of plane z - P1
     VecT d00, d01, d02;
+    vfma_to<T, V, PQ>(d00, prm.c2z[2 * P2], xc, q0[0]);
+    vfma_to<T, V, PQ>(d01, prm.c1z[2 * P1], gyv, q1[0]);
+    vfma_to<T, V, PQ>(d02, prm.c1z[2 * P1], gxc, q2[0]);
 #pragma unroll
-    for (int p = 0; p < V; ++p) {
-      d00.v[p] = fma(prm.c2z[2 * P2], xc[p], q0[0][p]);
-      d01.v[p] = fma(prm.c1z[2 * P1], gyv[p], q1[0][p]);
-      d02.v[p] = fma(prm.c1z[2 * P1], gxc[p], q2[0][p]);
+    for (int j = 1; j < 2 * P2; ++j) vfma_to<T, V, PQ>(q0[j - 1], prm.c2z[2 * P2 - j], xc, q0[j]);
+#pragma unroll
+    for (int j = 1; j < 2 * P1; ++j) {
+      vfma_to<T, V, PQ>(q1[j - 1], prm.c1z[2 * P1 - j], gyv, q1[j]);
+      vfma_to<T, V, PQ>(q2[j - 1], prm.c1z[2 * P1 - j], gxc, q2[j]);
     }
-#pragma unroll
-    for (int j = 1; j < 2 * P2; ++j)
-#pragma unroll
-      for (int p = 0; p < V; ++p) q0[j - 1][p] = fma(prm.c2z[2 * P2 - j], xc[p], q0[j][p]);
-#pragma unroll
-    for (int j = 1; j < 2 * P1; ++j)
-#pragma unroll
-      for (int p = 0; p < V; ++p) {
-        q1[j - 1][p] = fma(prm.c1z[2 * P1 - j], gyv[p], q1[j][p]);
-        q2[j - 1][p] = fma(prm.c1z[2 * P1 - j], gxc[p], q2[j][p]);
-      }
-#pragma unroll
-    for (int p = 0; p < V; ++p) {
-      q0[2 * P2 - 1][p] = prm.c2z[0] * xc[p];
-      q1[2 * P1 - 1][p] = prm.c1z[0] * gyv[p];
-      q2[2 * P1 - 1][p] = prm.c1z[0] * gxc[p];
-    }
+    vmul<T, V, PQ>(q0[2 * P2 - 1], prm.c2z[0], xc);
+    vmul<T, V, PQ>(q1[2 * P1 - 1], prm.c1z[0], gyv);
+    vmul<T, V, PQ>(q2[2 * P1 - 1], prm.c1z[0], gxc);
     const int zo2 = z - P2, zo = z - P1;
     if (zo2 >= zc0 && zo2 < zc1 && own) st_cs<T, V>(prm.h + (int64_t)zo2 * plane + ooff, d00, plain);  // key 0: (0,0)
     if (zo >= zc0 && zo < zc1 && own) {
