@@ -97,6 +97,8 @@ EXPORTS = (
     "fdx_axis_apply_dup_f64",
     "fdx_hessian3d_f32",
     "fdx_hessian3d_f64",
+    "fdx_hessian2d_f32",
+    "fdx_hessian2d_f64",
 )
 
 
@@ -135,6 +137,7 @@ def load():
             getattr(lib, f"fdx_axis_apply_{sfx}").argtypes = [vp, vp, vp, i64, i64, dbl, i32, vp]
             getattr(lib, f"fdx_axis_apply_dup_{sfx}").argtypes = [vp, vp, vp, vp, vp, i64, i64, dbl, vp]
             getattr(lib, f"fdx_hessian3d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, vp, C.POINTER(dbl), C.POINTER(dbl), vp]
+            getattr(lib, f"fdx_hessian2d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, vp, C.POINTER(dbl), C.POINTER(dbl), vp]
             getattr(lib, f"fdx_laplacian2d_{sfx}").argtypes = [C.POINTER(vp), vp, vp, C.POINTER(dbl), vp]
             getattr(lib, f"fdx_divergence2d_{sfx}").argtypes = [C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(dbl), vp]
             getattr(lib, f"fdx_gradient2d_{sfx}").argtypes = [C.POINTER(vp), vp, C.POINTER(vp), C.POINTER(dbl), vp]
@@ -319,6 +322,28 @@ def hessian3d(d1: Sequence[AxisPlan], d2: Sequence["AxisPlan | None"], x: torch.
         rc = fn(hp1, hp2, C.c_void_p(x.data_ptr()), C.c_void_p(h.data_ptr()), _alphas(a1), _alphas(a2), _stream_ptr(x.device))
     if rc != 0 and rc != -2:
         check(rc, "fdx_hessian3d")
+    return rc
+
+
+def hessian2d(d1: Sequence[AxisPlan], d2: Sequence[AxisPlan], x: torch.Tensor, h: torch.Tensor, a1: Sequence[float], a2: Sequence[float]) -> int:
+    """The fused 2-D hessian: ``h`` (2, 2, *x.shape) = [[F0, F1], [F1, F2]] in one pass over ``x``.  Returns 0, or -2 when the
+    fused kernel does not cover the call."""
+    _require(x, "x")
+    _require(h, "h")
+    assert x.ndim == 2 and tuple(h.shape) == (2, 2) + tuple(x.shape) and h.dtype == x.dtype
+    if x.numel() == 0:
+        return 0
+    k1 = [device_plan(p, x.device) for p in d1]
+    k2 = [device_plan(p, x.device) for p in d2]
+    hp1 = (C.c_void_p * 2)(*[dp.handle for dp in k1])
+    hp2 = (C.c_void_p * 2)(*[dp.handle for dp in k2])
+    al1 = (C.c_double * 2)(*[float(a) for a in a1])
+    al2 = (C.c_double * 2)(*[float(a) for a in a2])
+    with _on_device(x.device):
+        fn = getattr(load(), f"fdx_hessian2d_{_sfx(x)}")
+        rc = fn(hp1, hp2, C.c_void_p(x.data_ptr()), C.c_void_p(h.data_ptr()), al1, al2, _stream_ptr(x.device))
+    if rc != 0 and rc != -2:
+        check(rc, "fdx_hessian2d")
     return rc
 
 

@@ -625,9 +625,299 @@ int run_hess(const fdx_plan_t d1_in[3], const fdx_plan_t d2_in[3], const T* x, T
   }
 }
 
+
+// ---- 2-D hessian ------------------------------------------------------------------------------------------------------
+// hessian of a 2-D scalar field (finite_diff.py:460-529 with ndim = 2: F[0] = D2_0 x, F[1] = D_1 D_0 x, F[2] = D2_1 x, H =
+// [[F0, F1], [F1, F2]]) in one pass: 1 read + 4 writes per point (the composition of axis passes: 4 reads + 5 writes).
+// A WARP marches a strip of 32 vectors down axis 0; no shared data between warps, no block barrier:
+//   row y: the lane's window of the row (its vector and the halo vectors, L1-shared with the neighbour lanes) gives
+//          gx = D_1 x and D2_1 x of its vector; two shift-register queues along axis 0 (x -> D2_0 x, reach P2; gx -> D_0 gx,
+//          reach P1) complete rows y - P2 / y - P1;
+//   boundary columns of axis 1 (edge strips; the last strip is anchored at the end of the row): the columns under the band
+//          are broadcast from their owner lanes with shuffles, lane j evaluates band row j from a scaled table in shared
+//          memory and hands it to the owner of column j;
+//   boundary rows of axis 0: work items of their own -- the band row collapses the rows under it into ONE virtual row
+//          G = (row yb of D_0) x, and D_1 D_0 x = D_1 G: the in-row code runs on G's window and on row yb's.
+template <typename T, int P1>
+struct Hess2Params {
+  const T* x;
+  T* h;  // (2, 2, n0, n1)
+  int32_t n0, n1;
+  int32_t y_lo, y_hi;  // main rows of axis 0
+  int32_t rc, n_chunks, strips;
+  int64_t march_items, items;
+  T c2y[2 * P1 + 3], c2x[2 * P1 + 3], c1y[2 * P1 + 1], c1x[2 * P1 + 1];
+  XBand xb1, xb2;
+  AxisTab yt1, yt2;
+  double a1y, a2y;
+};
+
+template <typename T, int P1>
+__global__ void __launch_bounds__(128) hessian2d_kernel(const __grid_constant__ Hess2Params<T, P1> prm) {
+  constexpr int V = 16 / (int)sizeof(T), P2 = P1 + 1, W1 = 2 * P1 + 1, W2 = 2 * P2 + 1;
+  constexpr int HXV = (P2 + V - 1) / V, HX = HXV * V, WV = 1 + 2 * HXV, TX = 32 * V;
+  using VecT = Vec<T, V>;
+  __shared__ T bt[4][kXBandMax][kXBandW];  // band rows of axis 1: {D_1 left, D_1 right, D2_1 left, D2_1 right}, scaled
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int e = tid; e < 4 * kXBandMax * kXBandW; e += 128) {
+    const int t = e / (kXBandMax * kXBandW), j = (e / kXBandW) % kXBandMax, c = e % kXBandW;
+    const XBand& xb = t < 2 ? prm.xb1 : prm.xb2;
+    const bool left = (t & 1) == 0;
+    const int rows = left ? xb.nl : xb.nr, w = left ? xb.wl : xb.wr;
+    const double* tab = left ? xb.l : xb.r;
+    bt[t][j][c] = (j < rows && c < w) ? (T)(tab[j * w + c] * xb.alpha) : (T)0;
+  }
+  __syncthreads();
+  const int64_t item = (int64_t)blockIdx.x * 4 + (tid >> 5);
+  if (item >= prm.items) return;
+  const bool band_item = item >= prm.march_items;
+  const int64_t it = band_item ? item - prm.march_items : item;
+  const int strip = (int)(it % prm.strips), rest = (int)(it / prm.strips);
+  const int x0 = min(strip * TX, max(0, prm.n1 - TX));
+  const int xo = x0 + lane * V;
+  const bool own = xo < prm.n1;
+  const bool edge_l = x0 == 0 && (prm.xb1.nl > 0 || prm.xb2.nl > 0), edge_r = x0 + TX >= prm.n1 && (prm.xb1.nr > 0 || prm.xb2.nr > 0);
+  const int64_t N = (int64_t)prm.n0 * prm.n1;
+
+  // window of a row: the lane's vector and HXV vectors on either side (zero outside the row / the grid)
+  auto load_win = [&](int y, VecT (&w)[WV]) {
+    const bool yin = y >= 0 && y < prm.n0;
+    const T* row = prm.x + (yin ? (int64_t)y * prm.n1 : 0);
+#pragma unroll
+    for (int u = 0; u < WV; ++u) {
+      const int col = xo + (u - HXV) * V;
+      if (yin && col >= 0 && col < prm.n1) {
+        w[u] = ld_cached<T, V>(row + col);
+      } else {
+#pragma unroll
+        for (int p = 0; p < V; ++p) w[u].v[p] = (T)0;
+      }
+    }
+  };
+  // in-row work on a window: gx = D_1 (row), xx = D2_1 (row) of the lane's vector, boundary columns included
+  auto row_ops = [&](const VecT (&w)[WV], VecT& gx, VecT& xx) {
+    T f[WV * V];
+#pragma unroll
+    for (int u = 0; u < WV; ++u)
+#pragma unroll
+      for (int p = 0; p < V; ++p) f[u * V + p] = w[u].v[p];
+#pragma unroll
+    for (int p = 0; p < V; ++p) {
+      T a = (T)0, b = (T)0;
+#pragma unroll
+      for (int k = 0; k < W1; ++k) a = fma(prm.c1x[k], f[HX - P1 + p + k], a);
+#pragma unroll
+      for (int k = 0; k < W2; ++k) b = fma(prm.c2x[k], f[HX - P2 + p + k], b);
+      gx.v[p] = a, xx.v[p] = b;
+    }
+    if (edge_l | edge_r) {  // (warp-uniform)
+      const VecT& c = w[HXV];
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? !edge_l : !edge_r) continue;
+        const int nb1 = side == 0 ? prm.xb1.nl : prm.xb1.nr, nb2 = side == 0 ? prm.xb2.nl : prm.xb2.nr;
+        const int w1 = side == 0 ? prm.xb1.wl : prm.xb1.wr, w2 = side == 0 ? prm.xb2.wl : prm.xb2.wr;
+        const int wmax = max(w1, w2);
+        // lane j evaluates band row j of both plans; the columns under the bands come from their owner lanes
+        T a1 = (T)0, a2 = (T)0;
+        const int jl = min(lane, kXBandMax - 1);
+#pragma unroll
+        for (int cc = 0; cc < kXBandW; ++cc) {
+          if (cc >= wmax) break;
+          // column under tap cc of plan 1 / plan 2 (the right bands end at the last column: different first columns)
+          const int col1 = side == 0 ? cc : prm.n1 - w1 + cc - x0, col2 = side == 0 ? cc : prm.n1 - w2 + cc - x0;
+          const int l1 = max(0, min(col1, TX - 1)), l2 = max(0, min(col2, TX - 1));
+          T s1 = c.v[0], s2 = c.v[0];
+#pragma unroll
+          for (int p = 1; p < V; ++p) {
+            if (l1 % V == p) s1 = c.v[p];
+            if (l2 % V == p) s2 = c.v[p];
+          }
+          const T v1 = __shfl_sync(0xffffffffu, s1, l1 / V), v2 = __shfl_sync(0xffffffffu, s2, l2 / V);
+          const T k1 = cc < w1 ? bt[side][jl][cc] : (T)0, k2 = cc < w2 ? bt[2 + side][jl][cc] : (T)0;
+          a1 = fma(k1, k1 != (T)0 ? v1 : (T)0, a1);
+          a2 = fma(k2, k2 != (T)0 ? v2 : (T)0, a2);
+        }
+#pragma unroll
+        for (int j = 0; j < kXBandMax; ++j) {
+          const T r1 = __shfl_sync(0xffffffffu, a1, j), r2 = __shfl_sync(0xffffffffu, a2, j);
+          const int c1 = side == 0 ? j : prm.n1 - nb1 + j - x0, c2 = side == 0 ? j : prm.n1 - nb2 + j - x0;
+#pragma unroll
+          for (int p = 0; p < V; ++p) {
+            if (j < nb1 && lane == c1 / V && p == c1 % V) gx.v[p] = r1;
+            if (j < nb2 && lane == c2 / V && p == c2 % V) xx.v[p] = r2;
+          }
+        }
+      }
+    }
+  };
+  const int64_t ooff = xo;
+
+  if (band_item) {
+    // ---- a boundary row of axis 0
+    const int yi = rest;
+    const int yb = yi < prm.y_lo ? yi : prm.y_hi + (yi - prm.y_lo);
+    const RowOp r1 = row_of(prm.yt1, yb), r2 = row_of(prm.yt2, yb);
+    VecT g[WV], w[WV], yy;
+#pragma unroll
+    for (int u = 0; u < WV; ++u)
+#pragma unroll
+      for (int p = 0; p < V; ++p) g[u].v[p] = (T)0;
+#pragma unroll
+    for (int p = 0; p < V; ++p) yy.v[p] = (T)0;
+    for (int c = 0; c < r1.cnt; ++c) {
+      const T k = (T)(__ldg(r1.c + c) * prm.a1y);
+      if (k == (T)0) continue;
+      load_win(r1.s + c, w);
+#pragma unroll
+      for (int u = 0; u < WV; ++u)
+#pragma unroll
+        for (int p = 0; p < V; ++p) g[u].v[p] = fma(k, w[u].v[p], g[u].v[p]);
+    }
+    for (int c = 0; c < r2.cnt; ++c) {
+      const T k = (T)(__ldg(r2.c + c) * prm.a2y);
+      if (k == (T)0 || !own) continue;
+      const VecT v = ld_cached<T, V>(prm.x + (int64_t)(r2.s + c) * prm.n1 + xo);
+#pragma unroll
+      for (int p = 0; p < V; ++p) yy.v[p] = fma(k, v.v[p], yy.v[p]);
+    }
+    VecT mixed, xx, dummy;
+    row_ops(g, mixed, dummy);
+    load_win(yb, w);
+    row_ops(w, dummy, xx);
+    if (own) {
+      T* o = prm.h + (int64_t)yb * prm.n1 + ooff;
+      st_cs<T, V>(o, yy);
+      st_cs<T, V>(o + N, mixed);
+      st_cs<T, V>(o + 2 * N, mixed);
+      st_cs<T, V>(o + 3 * N, xx);
+    }
+    return;
+  }
+
+  // ---- a chunk of main rows
+  const int yc0 = prm.y_lo + rest * prm.rc, yc1 = min(yc0 + prm.rc, prm.y_hi);
+  VecT q0[2 * P2], q1[2 * P1];
+#pragma unroll
+  for (int j = 0; j < 2 * P2; ++j)
+#pragma unroll
+    for (int p = 0; p < V; ++p) q0[j].v[p] = (T)0;
+#pragma unroll
+  for (int j = 0; j < 2 * P1; ++j)
+#pragma unroll
+    for (int p = 0; p < V; ++p) q1[j].v[p] = (T)0;
+  VecT w[WV], wn[WV];
+  load_win(yc0 - P2, w);
+  for (int y = yc0 - P2; y <= yc1 - 1 + P2; ++y) {
+    if (y < yc1 - 1 + P2) load_win(y + 1, wn);  // (next row in flight behind this row's arithmetic)
+    VecT gx, xx;
+    row_ops(w, gx, xx);
+    const VecT& xc = w[HXV];
+    if (y >= yc0 && y < yc1 && own) st_cs<T, V>(prm.h + 3 * N + (int64_t)y * prm.n1 + ooff, xx);
+    VecT yy, mixed;
+    vfma_to<T, V>(yy, prm.c2y[2 * P2], xc, q0[0]);
+    vfma_to<T, V>(mixed, prm.c1y[2 * P1], gx, q1[0]);
+#pragma unroll
+    for (int j = 1; j < 2 * P2; ++j) vfma_to<T, V>(q0[j - 1], prm.c2y[2 * P2 - j], xc, q0[j]);
+#pragma unroll
+    for (int j = 1; j < 2 * P1; ++j) vfma_to<T, V>(q1[j - 1], prm.c1y[2 * P1 - j], gx, q1[j]);
+    vmul<T, V>(q0[2 * P2 - 1], prm.c2y[0], xc);
+    vmul<T, V>(q1[2 * P1 - 1], prm.c1y[0], gx);
+    const int yo2 = y - P2, yo1 = y - P1;
+    if (yo2 >= yc0 && yo2 < yc1 && own) st_cs<T, V>(prm.h + (int64_t)yo2 * prm.n1 + ooff, yy);
+    if (yo1 >= yc0 && yo1 < yc1 && own) {
+      T* o = prm.h + (int64_t)yo1 * prm.n1 + ooff;
+      st_cs<T, V>(o + N, mixed);
+      st_cs<T, V>(o + 2 * N, mixed);
+    }
+#pragma unroll
+    for (int u = 0; u < WV; ++u) w[u] = wn[u];
+  }
+}
+
+template <typename T, int P1>
+int launch_hess2(const fdx_plan_s* const d1[2], const fdx_plan_s* const d2[2], const T* x, T* h, const double a1[2], const double a2[2],
+                 int by0, int by1, cudaStream_t st) {
+  constexpr int V = 16 / (int)sizeof(T), TX = 32 * V;
+  Hess2Params<T, P1> prm;
+  prm.x = x, prm.h = h, prm.n0 = d1[0]->n, prm.n1 = d1[1]->n;
+  prm.y_lo = by0, prm.y_hi = by1;
+  fill_taps<T, P1 + 1>(prm.c2y, d2[0], a2[0]);
+  fill_taps<T, P1 + 1>(prm.c2x, d2[1], a2[1]);
+  fill_taps<T, P1>(prm.c1y, d1[0], a1[0]);
+  fill_taps<T, P1>(prm.c1x, d1[1], a1[1]);
+  prm.xb1 = XBand{d1[1]->band_l, d1[1]->band_r, d1[1]->nl, d1[1]->wl, d1[1]->nr, d1[1]->wr, a1[1]};
+  prm.xb2 = XBand{d2[1]->band_l, d2[1]->band_r, d2[1]->nl, d2[1]->wl, d2[1]->nr, d2[1]->wr, a2[1]};
+  prm.yt1 = tab_of(d1[0]), prm.yt2 = tab_of(d2[0]), prm.a1y = a1[0], prm.a2y = a2[0];
+  prm.strips = (prm.n1 + TX - 1) / TX;
+  const int ny = by1 - by0;
+  prm.rc = 1, prm.n_chunks = 0;
+  if (ny > 0) {
+    // rows per chunk: a chunk re-reads 2 P2 rows; ~32 warps per SM over the launch, at least 32 rows per chunk
+    const int64_t want = (int64_t)env_int("FDX_HESS2D_WPS", 32) * num_sms();
+    const int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((ny + 31) / 32, (want + prm.strips - 1) / prm.strips));
+    prm.rc = (int)((ny + chunks - 1) / chunks);
+    prm.n_chunks = (ny + prm.rc - 1) / prm.rc;
+  }
+  prm.march_items = (int64_t)prm.strips * prm.n_chunks;
+  prm.items = prm.march_items + (int64_t)prm.strips * (prm.n0 - ny);
+  const int64_t blocks = (prm.items + 3) / 4;
+  if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
+  if (blocks == 0) return FDX_OK;
+  hessian2d_kernel<T, P1><<<(unsigned)blocks, 128, 0, st>>>(prm);
+  count_launch("fused_hessian2d");
+  FDX_LAUNCH_CHECK();
+  return FDX_OK;
+}
+
+template <typename T>
+int run_hess2(const fdx_plan_t d1_in[2], const fdx_plan_t d2_in[2], const T* x, T* h, const double a1[2], const double a2[2], void* stream) {
+  constexpr int V = 16 / (int)sizeof(T);
+  if (!d1_in || !d2_in || !a1 || !a2 || !x || !h) return FDX_EINVAL;
+  if (!d1_in[0] || !d1_in[1] || !d2_in[0] || !d2_in[1]) return FDX_EINVAL;
+  if (env_int("FDX_HESS_DISABLE", 0)) return FDX_EUNSUPPORTED;
+  const fdx_plan_s* d1[2] = {d1_in[0], d1_in[1]};
+  const fdx_plan_s* d2[2] = {d2_in[0], d2_in[1]};
+  if (d2[0]->n != d1[0]->n || d2[1]->n != d1[1]->n) return FDX_EINVAL;
+  const int n0 = d1[0]->n, n1 = d1[1]->n;
+  if (n0 == 0 || n1 == 0) return FDX_OK;
+  const fdx_plan_s* all[4] = {d1[0], d1[1], d2[0], d2[1]};
+  int P1 = 1;
+  for (int k = 0; k < 4; ++k) {
+    const fdx_plan_s* p = all[k];
+    if (p->nl + p->nr > p->n) return FDX_EUNSUPPORTED;
+    if (p->nl < -p->lo || p->nr < p->hi) return FDX_EUNSUPPORTED;
+    if (p->wl > p->n || p->wr > p->n) return FDX_EUNSUPPORTED;
+    const int reach = std::max(std::abs(p->lo), std::abs(p->hi));
+    P1 = std::max(P1, k < 2 ? reach : reach - 1);
+  }
+  if (P1 > 3) return FDX_EUNSUPPORTED;
+  if (n1 % V != 0 || ((uintptr_t)x & 15) != 0 || ((uintptr_t)h & 15) != 0) return FDX_EUNSUPPORTED;
+  if (((int64_t)n0 * n1) % V != 0) return FDX_EUNSUPPORTED;
+  if (std::max(d1[1]->nl, d2[1]->nl) > kXBandMax || std::max(d1[1]->nr, d2[1]->nr) > kXBandMax) return FDX_EUNSUPPORTED;
+  if (std::max(std::max(d1[1]->wl, d2[1]->wl), std::max(d1[1]->wr, d2[1]->wr)) > kXBandW) return FDX_EUNSUPPORTED;
+  if (std::max(std::max(d1[1]->wl, d2[1]->wl), std::max(d1[1]->wr, d2[1]->wr)) > 32 * V) return FDX_EUNSUPPORTED;
+  int by0 = std::max(d1[0]->nl, d2[0]->nl), by1 = n0 - std::max(d1[0]->nr, d2[0]->nr);
+  if (by1 < by0) by1 = by0;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (P1) {
+    case 1: return launch_hess2<T, 1>(d1, d2, x, h, a1, a2, by0, by1, st);
+    case 2: return launch_hess2<T, 2>(d1, d2, x, h, a1, a2, by0, by1, st);
+    default: return launch_hess2<T, 3>(d1, d2, x, h, a1, a2, by0, by1, st);
+  }
+}
+
 }  // namespace
 }  // namespace fdx
 
+extern "C" int fdx_hessian2d_f32(const fdx_plan_t d1[2], const fdx_plan_t d2[2], const float* x, float* h, const double a1[2],
+                                 const double a2[2], void* stream) {
+  return fdx::run_hess2<float>(d1, d2, x, h, a1, a2, stream);
+}
+extern "C" int fdx_hessian2d_f64(const fdx_plan_t d1[2], const fdx_plan_t d2[2], const double* x, double* h, const double a1[2],
+                                 const double a2[2], void* stream) {
+  return fdx::run_hess2<double>(d1, d2, x, h, a1, a2, stream);
+}
 extern "C" int fdx_hessian3d_f32(const fdx_plan_t d1[3], const fdx_plan_t d2[3], const float* x, float* h, const double a1[3],
                                  const double a2[3], void* stream) {
   return fdx::run_hess<float>(d1, d2, x, h, a1, a2, stream);

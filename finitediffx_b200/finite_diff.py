@@ -688,6 +688,11 @@ def hessian(array, *, accuracy=2, step_size=1, method: MethodKind = "central"):
         a2 = [_alpha(step_size[k], 2) for k in range(3)]
         if _cabi.hessian3d(p1, p2, x, out, a1, a2) == 0:
             return restore(out)
+    if nd == 2:
+        p1 = [d1(k).plan(x.shape[k]) for k in range(2)]
+        p2 = [d2(k).plan(x.shape[k]) for k in range(2)]
+        if _cabi.hessian2d(p1, p2, x, out, [_alpha(step_size[k], 1) for k in range(2)], [_alpha(step_size[k], 2) for k in range(2)]) == 0:
+            return restore(out)
     first = {}
     for key, who in producer.items():
         slots = [(i, key - i) for i in range(nd) if 0 <= key - i < nd]

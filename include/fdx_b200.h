@@ -156,6 +156,13 @@ int fdx_hessian3d_f32(const fdx_plan_t d1[3], const fdx_plan_t d2[3], const floa
 int fdx_hessian3d_f64(const fdx_plan_t d1[3], const fdx_plan_t d2[3], const double* x, double* h, const double a1[3],
                       const double a2[3], void* stream);
 
+/* the 2-D form (ndim = 2: F[0] = a2[0] D2_0 x, F[1] = a1[0] a1[1] D_1 D_0 x, F[2] = a2[1] D2_1 x; h is (2, 2, n0, n1) with
+ * H = [[F0, F1], [F1, F2]]): one pass, 1 read + 4 writes per point.  Same coverage rules. */
+int fdx_hessian2d_f32(const fdx_plan_t d1[2], const fdx_plan_t d2[2], const float* x, float* h, const double a1[2],
+                      const double a2[2], void* stream);
+int fdx_hessian2d_f64(const fdx_plan_t d1[2], const fdx_plan_t d2[2], const double* x, double* h, const double a1[2],
+                      const double a2[2], void* stream);
+
 /* ---- scale read on the device.  The reference traces `step_size` (finite_diff.py:168), so inside a jitted caller
  * alpha = 1 / step_size**derivative is a DEVICE value; an XLA custom call must not fetch it.  `alpha_dev` is a device
  * pointer to float64: one value for the axis operator (out = sign * alpha_dev[0] * D x), three (one per axis) for the

@@ -834,6 +834,48 @@ def test_fused_hessian3d_vs_oracle(dtype):
     assert parity_error("hessian", x, kw, out, O.hessian(x, **kw)) <= TOL[np.dtype(dtype)]
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fused_hessian2d_vs_oracle(dtype):
+    """The one-pass 2-D hessian (fdx_hessian2d: a warp per strip marching down axis 0, band columns by shuffles, band rows as
+    items of their own) against the oracle, including the reference's own test shape (tests/test_finite_diff.py:286-307:
+    100 x 100, accuracy 4)."""
+    rng = np.random.default_rng(12)
+    cases = [
+        ((100, 100), dict(accuracy=4, step_size=(0.02, 0.03))),
+        ((40, 48), dict(accuracy=2, step_size=0.5)),
+        ((37, 264), dict(accuracy=4, step_size=(0.1, 0.2))),       # three strips in fp32, the last one anchored
+        ((90, 20), dict(accuracy=(2, 6), step_size=0.25)),
+        ((33, 36), dict(accuracy=6, step_size=0.5)),
+        ((64, 132), dict(accuracy=(3, 2), step_size=(0.3, 0.1))),
+        ((300, 16), dict(accuracy=2, step_size=0.1)),               # several chunks of rows
+    ]
+    for method in ("central", "forward", "backward"):
+        for shape, kw in cases:
+            acc = kw["accuracy"]
+            amax = max(acc) if isinstance(acc, tuple) else acc
+            if method != "central" and amax > 3:
+                continue
+            kw = dict(kw, method=method)
+            x = rng.standard_normal(shape).astype(dtype)
+            with _env(FDX_HESS2D_WPS=1 if shape[0] == 300 else 32):
+                out = _call("hessian", x, **kw)
+            assert _cabi.last_kernel() == "fused_hessian2d", (shape, kw, _cabi.last_kernel())
+            ref = O.hessian(x, **kw)
+            assert out.shape == ref.shape and out.dtype == ref.dtype
+            err = parity_error("hessian", x, kw, out, ref)
+            assert err <= TOL[np.dtype(dtype)], (shape, kw, err)
+            assert np.array_equal(out[0, 1], out[1, 0])
+    x = torch.randn((1024, 2048), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    kw = dict(accuracy=4, step_size=(0.1, 0.2))
+    h = fdx.hessian(x, **kw)
+    assert _cabi.last_kernel() == "fused_hessian2d"
+    with _env(FDX_HESS_DISABLE=1):
+        h0 = fdx.hessian(x, **kw)
+    assert _cabi.last_kernel() != "fused_hessian2d"
+    sc = h0.abs().amax(dim=(2, 3), keepdim=True)
+    assert ((h - h0).abs() / sc).max().item() <= 2e-5
+
+
 def test_fused_hessian3d_against_the_composition_on_a_big_grid():
     """Fused one-pass hessian == the 7-pass composition of axis kernels within the parity bound (the nesting order of the
     mixed entries differs, the boundary rows are the same dense rows), on a grid of several chunks and tiles; inf in the
