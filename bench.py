@@ -617,6 +617,8 @@ def _extras_single(fdx, _cabi, dev, peak):
                                     ("curl2d_8192sq_f32_a4", lambda v: fdx.curl(v, accuracy=4, step_size=0.1), f2, 3)):
         t = timed(call, [arr], k=10, wu=3)
         ex[name] = _entry(pts, 4 * fields, t, peak, _cabi.last_kernel())
+    t = timed(lambda v: fdx.hessian(v, accuracy=4, step_size=0.1), [x], k=10, wu=3)
+    ex["hessian2d_8192sq_f32_a4"] = _entry(pts, 4 * (1 + 4), t, peak, _cabi.last_kernel(), note="ONE fused launch (fdx_hessian2d); one read + four writes")
     del x, f2
     torch.cuda.empty_cache()
     # ---- jacobian and hessian on 3-D grids (algorithmic bytes: one read per input field, one write per output field)

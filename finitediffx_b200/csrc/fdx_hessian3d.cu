@@ -80,6 +80,7 @@ struct XBand {
 constexpr int kXBandMax = 4;  // band columns per side the march handles (reach of the second derivative <= 4)
 constexpr int kXBandW = 12;   // taps per band row (first-derivative reach <= 3: wl <= 4 + 7)
 constexpr int kYBandMax = 3;  // band rows of axis 1 per side (first-derivative reach <= 3)
+constexpr int kXBandW2 = 16;  // 2-D kernel: taps per band row incl. the shift of a right band to a vector boundary
 
 // One band element: kXBandW taps from the CTA's table in shared memory (scaled, zero-padded) over a staged row; `row`
 // points at the staged element under the band's first column, `w` is the band's width (lanes past it re-read its last
@@ -653,34 +654,16 @@ struct Hess2Params {
 };
 
 template <typename T, int P1>
-__global__ void __launch_bounds__(128) hessian2d_kernel(const __grid_constant__ Hess2Params<T, P1> prm) {
-  constexpr int V = 16 / (int)sizeof(T), P2 = P1 + 1, W1 = 2 * P1 + 1, W2 = 2 * P2 + 1;
-  constexpr int HXV = (P2 + V - 1) / V, HX = HXV * V, WV = 1 + 2 * HXV, TX = 32 * V;
-  using VecT = Vec<T, V>;
-  __shared__ T bt[4][kXBandMax][kXBandW];  // band rows of axis 1: {D_1 left, D_1 right, D2_1 left, D2_1 right}, scaled
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int e = tid; e < 4 * kXBandMax * kXBandW; e += 128) {
-    const int t = e / (kXBandMax * kXBandW), j = (e / kXBandW) % kXBandMax, c = e % kXBandW;
-    const XBand& xb = t < 2 ? prm.xb1 : prm.xb2;
-    const bool left = (t & 1) == 0;
-    const int rows = left ? xb.nl : xb.nr, w = left ? xb.wl : xb.wr;
-    const double* tab = left ? xb.l : xb.r;
-    bt[t][j][c] = (j < rows && c < w) ? (T)(tab[j * w + c] * xb.alpha) : (T)0;
-  }
-  __syncthreads();
-  const int64_t item = (int64_t)blockIdx.x * 4 + (tid >> 5);
-  if (item >= prm.items) return;
-  const bool band_item = item >= prm.march_items;
-  const int64_t it = band_item ? item - prm.march_items : item;
-  const int strip = (int)(it % prm.strips), rest = (int)(it / prm.strips);
-  const int x0 = min(strip * TX, max(0, prm.n1 - TX));
-  const int xo = x0 + lane * V;
-  const bool own = xo < prm.n1;
-  const bool edge_l = x0 == 0 && (prm.xb1.nl > 0 || prm.xb2.nl > 0), edge_r = x0 + TX >= prm.n1 && (prm.xb1.nr > 0 || prm.xb2.nr > 0);
-  const int64_t N = (int64_t)prm.n0 * prm.n1;
+struct Hess2Geom {
+  static constexpr int V = 16 / (int)sizeof(T), P2 = P1 + 1, W1 = 2 * P1 + 1, W2 = 2 * P2 + 1;
+  static constexpr int HXV = (P2 + V - 1) / V, HX = HXV * V, WV = 1 + 2 * HXV, TX = 32 * V;
+};
+// window of a row: the lane's vector and HXV vectors on either side (zero outside the row / the grid)
+template <typename T, int P1>
+__device__ __forceinline__ void h2_load_win(const Hess2Params<T, P1>& prm, int xo, int y, Vec<T, 16 / (int)sizeof(T)> (&w)[Hess2Geom<T, P1>::WV]) {
+  using G = Hess2Geom<T, P1>;
+  constexpr int V = G::V, HXV = G::HXV, WV = G::WV;
 
-  // window of a row: the lane's vector and HXV vectors on either side (zero outside the row / the grid)
-  auto load_win = [&](int y, VecT (&w)[WV]) {
     const bool yin = y >= 0 && y < prm.n0;
     const T* row = prm.x + (yin ? (int64_t)y * prm.n1 : 0);
 #pragma unroll
@@ -693,9 +676,16 @@ __global__ void __launch_bounds__(128) hessian2d_kernel(const __grid_constant__ 
         for (int p = 0; p < V; ++p) w[u].v[p] = (T)0;
       }
     }
-  };
-  // in-row work on a window: gx = D_1 (row), xx = D2_1 (row) of the lane's vector, boundary columns included
-  auto row_ops = [&](const VecT (&w)[WV], VecT& gx, VecT& xx) {
+}
+// in-row work on a window: gx = D_1 (row), xx = D2_1 (row) of the lane's vector, boundary columns included
+template <typename T, int P1>
+__device__ __forceinline__ void h2_row_ops(const Hess2Params<T, P1>& prm, const T (*bt)[kXBandMax][kXBandW2], int x0, int lane, bool edge_l,
+                                           bool edge_r, const Vec<T, 16 / (int)sizeof(T)> (&w)[Hess2Geom<T, P1>::WV],
+                                           Vec<T, 16 / (int)sizeof(T)>& gx, Vec<T, 16 / (int)sizeof(T)>& xx) {
+  using G = Hess2Geom<T, P1>;
+  constexpr int V = G::V, P2 = G::P2, W1 = G::W1, W2 = G::W2, HXV = G::HXV, HX = G::HX, WV = G::WV, TX = G::TX;
+  using VecT = Vec<T, V>;
+
     T f[WV * V];
 #pragma unroll
     for (int u = 0; u < WV; ++u)
@@ -717,40 +707,67 @@ __global__ void __launch_bounds__(128) hessian2d_kernel(const __grid_constant__ 
         if (side == 0 ? !edge_l : !edge_r) continue;
         const int nb1 = side == 0 ? prm.xb1.nl : prm.xb1.nr, nb2 = side == 0 ? prm.xb2.nl : prm.xb2.nr;
         const int w1 = side == 0 ? prm.xb1.wl : prm.xb1.wr, w2 = side == 0 ? prm.xb2.wl : prm.xb2.wr;
-        const int wmax = max(w1, w2);
+        // the table of a right band starts at the vector boundary at or below its first column (leading zero taps), so
+        // that tap cc always sits in element cc % V of its owner lane: every register index below is static
+        const int f1 = side == 0 ? 0 : (prm.n1 - w1) / V * V, f2 = side == 0 ? 0 : (prm.n1 - w2) / V * V;
+        const int e1 = side == 0 ? w1 : prm.n1 - f1, e2 = side == 0 ? w2 : prm.n1 - f2;  // taps of the shifted tables
+        const int emax = max(e1, e2);
+        const int s1 = (f1 - x0) / V, s2 = (f2 - x0) / V;  // lanes of the first vectors under the bands
         // lane j evaluates band row j of both plans; the columns under the bands come from their owner lanes
         T a1 = (T)0, a2 = (T)0;
         const int jl = min(lane, kXBandMax - 1);
 #pragma unroll
-        for (int cc = 0; cc < kXBandW; ++cc) {
-          if (cc >= wmax) break;
-          // column under tap cc of plan 1 / plan 2 (the right bands end at the last column: different first columns)
-          const int col1 = side == 0 ? cc : prm.n1 - w1 + cc - x0, col2 = side == 0 ? cc : prm.n1 - w2 + cc - x0;
-          const int l1 = max(0, min(col1, TX - 1)), l2 = max(0, min(col2, TX - 1));
-          T s1 = c.v[0], s2 = c.v[0];
-#pragma unroll
-          for (int p = 1; p < V; ++p) {
-            if (l1 % V == p) s1 = c.v[p];
-            if (l2 % V == p) s2 = c.v[p];
-          }
-          const T v1 = __shfl_sync(0xffffffffu, s1, l1 / V), v2 = __shfl_sync(0xffffffffu, s2, l2 / V);
-          const T k1 = cc < w1 ? bt[side][jl][cc] : (T)0, k2 = cc < w2 ? bt[2 + side][jl][cc] : (T)0;
+        for (int cc = 0; cc < kXBandW2; ++cc) {
+          if (cc >= emax) break;
+          const T v1 = __shfl_sync(0xffffffffu, c.v[cc % V], min(s1 + cc / V, 31));
+          const T v2 = __shfl_sync(0xffffffffu, c.v[cc % V], min(s2 + cc / V, 31));
+          const T k1 = bt[side][jl][cc], k2 = bt[2 + side][jl][cc];
           a1 = fma(k1, k1 != (T)0 ? v1 : (T)0, a1);
           a2 = fma(k2, k2 != (T)0 ? v2 : (T)0, a2);
         }
+        // the owner of a band column fetches its value from the lane that evaluated its band row
+        const int b1 = side == 0 ? 0 : prm.n1 - nb1, b2 = side == 0 ? 0 : prm.n1 - nb2;  // first band columns
 #pragma unroll
-        for (int j = 0; j < kXBandMax; ++j) {
-          const T r1 = __shfl_sync(0xffffffffu, a1, j), r2 = __shfl_sync(0xffffffffu, a2, j);
-          const int c1 = side == 0 ? j : prm.n1 - nb1 + j - x0, c2 = side == 0 ? j : prm.n1 - nb2 + j - x0;
-#pragma unroll
-          for (int p = 0; p < V; ++p) {
-            if (j < nb1 && lane == c1 / V && p == c1 % V) gx.v[p] = r1;
-            if (j < nb2 && lane == c2 / V && p == c2 % V) xx.v[p] = r2;
-          }
+        for (int p = 0; p < V; ++p) {
+          const int col = x0 + lane * V + p;
+          const int j1 = col - b1, j2 = col - b2;
+          const T r1 = __shfl_sync(0xffffffffu, a1, max(0, min(j1, 31))), r2 = __shfl_sync(0xffffffffu, a2, max(0, min(j2, 31)));
+          if (j1 >= 0 && j1 < nb1 && col < prm.n1) gx.v[p] = r1;
+          if (j2 >= 0 && j2 < nb2 && col < prm.n1) xx.v[p] = r2;
         }
       }
     }
-  };
+}
+
+template <typename T, int P1, int MINB>
+__global__ void __launch_bounds__(128, MINB) hessian2d_kernel(const __grid_constant__ Hess2Params<T, P1> prm) {
+  constexpr int V = 16 / (int)sizeof(T), P2 = P1 + 1, W1 = 2 * P1 + 1, W2 = 2 * P2 + 1;
+  constexpr int HXV = (P2 + V - 1) / V, HX = HXV * V, WV = 1 + 2 * HXV, TX = 32 * V;
+  using VecT = Vec<T, V>;
+  __shared__ T bt[4][kXBandMax][kXBandW2];  // band rows of axis 1: {D_1 left, D_1 right, D2_1 left, D2_1 right}, scaled
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int e = tid; e < 4 * kXBandMax * kXBandW2; e += 128) {
+    const int t = e / (kXBandMax * kXBandW2), j = (e / kXBandW2) % kXBandMax, cc = e % kXBandW2;
+    const XBand& xb = t < 2 ? prm.xb1 : prm.xb2;
+    const bool left = (t & 1) == 0;
+    const int rows = left ? xb.nl : xb.nr, w = left ? xb.wl : xb.wr;
+    const int off = left ? 0 : (prm.n1 - w) % V;  // (right bands: shifted to the vector boundary below their first column)
+    const double* tab = left ? xb.l : xb.r;
+    const int c = cc - off;
+    bt[t][j][cc] = (j < rows && c >= 0 && c < w) ? (T)(tab[j * w + c] * xb.alpha) : (T)0;
+  }
+  __syncthreads();
+  const int64_t item = (int64_t)blockIdx.x * 4 + (tid >> 5);
+  if (item >= prm.items) return;
+  const bool band_item = item >= prm.march_items;
+  const int64_t it = band_item ? item - prm.march_items : item;
+  const int strip = (int)(it % prm.strips), rest = (int)(it / prm.strips);
+  const int x0 = min(strip * TX, max(0, prm.n1 - TX));
+  const int xo = x0 + lane * V;
+  const bool own = xo < prm.n1;
+  const bool edge_l = x0 == 0 && (prm.xb1.nl > 0 || prm.xb2.nl > 0), edge_r = x0 + TX >= prm.n1 && (prm.xb1.nr > 0 || prm.xb2.nr > 0);
+  const int64_t N = (int64_t)prm.n0 * prm.n1;
+
   const int64_t ooff = xo;
 
   if (band_item) {
@@ -768,7 +785,7 @@ __global__ void __launch_bounds__(128) hessian2d_kernel(const __grid_constant__ 
     for (int c = 0; c < r1.cnt; ++c) {
       const T k = (T)(__ldg(r1.c + c) * prm.a1y);
       if (k == (T)0) continue;
-      load_win(r1.s + c, w);
+      h2_load_win<T, P1>(prm, xo, r1.s + c, w);
 #pragma unroll
       for (int u = 0; u < WV; ++u)
 #pragma unroll
@@ -782,9 +799,9 @@ __global__ void __launch_bounds__(128) hessian2d_kernel(const __grid_constant__ 
       for (int p = 0; p < V; ++p) yy.v[p] = fma(k, v.v[p], yy.v[p]);
     }
     VecT mixed, xx, dummy;
-    row_ops(g, mixed, dummy);
-    load_win(yb, w);
-    row_ops(w, dummy, xx);
+    h2_row_ops<T, P1>(prm, bt, x0, lane, edge_l, edge_r, g, mixed, dummy);
+    h2_load_win<T, P1>(prm, xo, yb, w);
+    h2_row_ops<T, P1>(prm, bt, x0, lane, edge_l, edge_r, w, dummy, xx);
     if (own) {
       T* o = prm.h + (int64_t)yb * prm.n1 + ooff;
       st_cs<T, V>(o, yy);
@@ -807,11 +824,11 @@ __global__ void __launch_bounds__(128) hessian2d_kernel(const __grid_constant__ 
 #pragma unroll
     for (int p = 0; p < V; ++p) q1[j].v[p] = (T)0;
   VecT w[WV], wn[WV];
-  load_win(yc0 - P2, w);
+  h2_load_win<T, P1>(prm, xo, yc0 - P2, w);
   for (int y = yc0 - P2; y <= yc1 - 1 + P2; ++y) {
-    if (y < yc1 - 1 + P2) load_win(y + 1, wn);  // (next row in flight behind this row's arithmetic)
+    if (y < yc1 - 1 + P2) h2_load_win<T, P1>(prm, xo, y + 1, wn);  // (next row in flight behind this row's arithmetic)
     VecT gx, xx;
-    row_ops(w, gx, xx);
+    h2_row_ops<T, P1>(prm, bt, x0, lane, edge_l, edge_r, w, gx, xx);
     const VecT& xc = w[HXV];
     if (y >= yc0 && y < yc1 && own) st_cs<T, V>(prm.h + 3 * N + (int64_t)y * prm.n1 + ooff, xx);
     VecT yy, mixed;
@@ -864,7 +881,9 @@ int launch_hess2(const fdx_plan_s* const d1[2], const fdx_plan_s* const d2[2], c
   const int64_t blocks = (prm.items + 3) / 4;
   if (blocks > 0x7fffffffLL) return FDX_EUNSUPPORTED;
   if (blocks == 0) return FDX_OK;
-  hessian2d_kernel<T, P1><<<(unsigned)blocks, 128, 0, st>>>(prm);
+  // 4 CTAs (16 warps) per SM at 128 registers: 8192^2 accuracy 4 fp32 0.347 ms against 0.406 (3 CTAs, 150 registers) and
+  // 0.506 (6 CTAs, 80 registers, spills); fp64 0.616 / 0.727 / 1.78
+  hessian2d_kernel<T, P1, 4><<<(unsigned)blocks, 128, 0, st>>>(prm);
   count_launch("fused_hessian2d");
   FDX_LAUNCH_CHECK();
   return FDX_OK;
