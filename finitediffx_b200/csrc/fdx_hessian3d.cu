@@ -646,6 +646,7 @@ struct Hess2Params {
   int32_t n0, n1;
   int32_t y_lo, y_hi;  // main rows of axis 0
   int32_t rc, n_chunks, strips;
+  int32_t pf;  // rows ahead of the march whose lines are pulled into L2 (prefetch.global.L2: no registers held)
   int64_t march_items, items;
   T c2y[2 * P1 + 3], c2x[2 * P1 + 3], c1y[2 * P1 + 1], c1x[2 * P1 + 1];
   XBand xb1, xb2;
@@ -827,6 +828,8 @@ __global__ void __launch_bounds__(128, MINB) hessian2d_kernel(const __grid_const
   h2_load_win<T, P1>(prm, xo, yc0 - P2, w);
   for (int y = yc0 - P2; y <= yc1 - 1 + P2; ++y) {
     if (y < yc1 - 1 + P2) h2_load_win<T, P1>(prm, xo, y + 1, wn);  // (next row in flight behind this row's arithmetic)
+    if (prm.pf > 0 && y + prm.pf < prm.n0 && y + prm.pf >= 0 && own)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.x + (int64_t)(y + prm.pf) * prm.n1 + xo));
     VecT gx, xx;
     h2_row_ops<T, P1>(prm, bt, x0, lane, edge_l, edge_r, w, gx, xx);
     const VecT& xc = w[HXV];
@@ -869,6 +872,8 @@ int launch_hess2(const fdx_plan_s* const d1[2], const fdx_plan_s* const d2[2], c
   prm.strips = (prm.n1 + TX - 1) / TX;
   const int ny = by1 - by0;
   prm.rc = 1, prm.n_chunks = 0;
+  // (8192^2 accuracy 4, rows ahead 0 / 2 / 4 / 8 / 16: fp32 0.416 / 0.332 / 0.318 / 0.340 / 0.382 ms, fp64 0.645 / 0.555 / 0.598 / 0.623 / 0.634)
+  prm.pf = env_int("FDX_HESS2D_PF", sizeof(T) == 4 ? 4 : 2);
   if (ny > 0) {
     // rows per chunk: a chunk re-reads 2 P2 rows; ~32 warps per SM over the launch, at least 32 rows per chunk
     const int64_t want = (int64_t)env_int("FDX_HESS2D_WPS", 32) * num_sms();

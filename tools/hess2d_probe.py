@@ -15,9 +15,8 @@ def main():
     for dt in (torch.float32, torch.float64):
         x = torch.randn((n, n), device="cuda", dtype=dt)
         gb = 5 * x.element_size() * n * n / 1e9
-        for env in ({"FDX_HESS_DISABLE": "1"}, {}, {"FDX_HESS2D_MINB": "3"}, {"FDX_HESS2D_MINB": "6"}, {"FDX_HESS2D_WPS": "64"}, {"FDX_HESS2D_WPS": "128"},
-                    {"FDX_HESS2D_WPS": "128", "FDX_HESS2D_MINB": "6"}):
-            for k in ("FDX_HESS_DISABLE", "FDX_HESS2D_WPS", "FDX_HESS2D_MINB"):
+        for env in ({"FDX_HESS_DISABLE": "1"}, {"FDX_HESS2D_PF": "0"}, {"FDX_HESS2D_PF": "2"}, {"FDX_HESS2D_PF": "4"}, {"FDX_HESS2D_PF": "8"}, {"FDX_HESS2D_PF": "16"}):
+            for k in ("FDX_HESS_DISABLE", "FDX_HESS2D_WPS", "FDX_HESS2D_MINB", "FDX_HESS2D_PF"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             _cabi.reload_env()
