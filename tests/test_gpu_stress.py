@@ -175,3 +175,48 @@ def test_fused_hessian3d_random_shapes_against_the_composition():
         assert err <= (3e-5 if dtype == torch.float32 else 1e-11), (case, shape, kw, zc, err)
     assert fused >= 80, fused
 
+
+def test_fused_hessian2d_random_shapes_against_the_composition():
+    """Random 2-D hessians: the one-pass kernel (fdx_hessian2d: strips, anchored last strip, band columns by shuffles, band
+    rows as items of their own, several chunks of rows) against the composition of axis kernels."""
+    import numpy as np
+
+    rnd = np.random.default_rng(77)
+    fused = 0
+    for case in range(120):
+        dtype = torch.float32 if case % 3 else torch.float64
+        method = ("central", "forward", "backward")[int(rnd.integers(0, 3))]
+        amax = 6 if method == "central" else 3
+        acc = tuple(int(a) for a in rnd.integers(1 if method != "central" else 2, amax + 1, size=2))
+        if rnd.random() < 0.4:
+            acc = acc[0]
+        v = 4 if dtype == torch.float32 else 2
+        lo = 2 * (amax + 2)
+        shape = (int(rnd.integers(lo, 200)), int(rnd.integers(lo // v + 1, 600 // v)) * v)
+        steps = tuple(float(h) for h in rnd.uniform(0.1, 1.0, size=2))
+        kw = dict(accuracy=acc, step_size=steps, method=method)
+        x = torch.randn(shape, device="cuda", dtype=dtype, generator=torch.Generator(device="cuda").manual_seed(case))
+        os.environ["FDX_HESS2D_WPS"] = str(int(rnd.choice([32, 1, 1000])))
+        _cabi.reload_env()
+        try:
+            try:
+                h = fdx.hessian(x, **kw)
+            except ValueError:
+                continue
+            kern = _cabi.last_kernel()
+            os.environ["FDX_HESS_DISABLE"] = "1"
+            _cabi.reload_env()
+            h0 = fdx.hessian(x, **kw)
+            assert _cabi.last_kernel() != "fused_hessian2d"
+        finally:
+            os.environ.pop("FDX_HESS_DISABLE", None)
+            os.environ.pop("FDX_HESS2D_WPS", None)
+            _cabi.reload_env()
+        if kern != "fused_hessian2d":
+            continue
+        fused += 1
+        sc = h0.abs().amax(dim=(2, 3), keepdim=True).clamp_min(1e-30)
+        err = ((h - h0).abs() / sc).max().item()
+        assert err <= (3e-5 if dtype == torch.float32 else 1e-11), (case, shape, kw, err)
+    assert fused >= 80, fused
+
