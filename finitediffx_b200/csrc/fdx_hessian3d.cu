@@ -888,7 +888,9 @@ int launch_hess2(const fdx_plan_s* const d1[2], const fdx_plan_s* const d2[2], c
   if (blocks == 0) return FDX_OK;
   // 4 CTAs (16 warps) per SM at 128 registers: 8192^2 accuracy 4 fp32 0.347 ms against 0.406 (3 CTAs, 150 registers) and
   // 0.506 (6 CTAs, 80 registers, spills); fp64 0.616 / 0.727 / 1.78
-  hessian2d_kernel<T, P1, 4><<<(unsigned)blocks, 128, 0, st>>>(prm);
+  // (fp64 at reach 3 spills at 128 registers and then loses to the composition: 3 CTAs per SM there)
+  constexpr int MB = (sizeof(T) == 8 && P1 == 3) ? 3 : 4;
+  hessian2d_kernel<T, P1, MB><<<(unsigned)blocks, 128, 0, st>>>(prm);
   count_launch("fused_hessian2d");
   FDX_LAUNCH_CHECK();
   return FDX_OK;
