@@ -873,7 +873,8 @@ int launch_hess2(const fdx_plan_s* const d1[2], const fdx_plan_s* const d2[2], c
   const int ny = by1 - by0;
   prm.rc = 1, prm.n_chunks = 0;
   // (8192^2 accuracy 4, rows ahead 0 / 2 / 4 / 8 / 16: fp32 0.416 / 0.332 / 0.318 / 0.340 / 0.382 ms, fp64 0.645 / 0.555 / 0.598 / 0.623 / 0.634)
-  prm.pf = env_int("FDX_HESS2D_PF", sizeof(T) == 4 ? 4 : 2);
+  // fp64, 2 against 4 rows ahead: accuracy 2 0.597 / 0.565, accuracy 4 0.555 / 0.598, accuracy 6 0.699 / 0.658 ms: 4 for both types
+  prm.pf = env_int("FDX_HESS2D_PF", 4);
   if (ny > 0) {
     // rows per chunk: a chunk re-reads 2 P2 rows; ~32 warps per SM over the launch, at least 32 rows per chunk
     const int64_t want = (int64_t)env_int("FDX_HESS2D_WPS", 32) * num_sms();
