@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
   const int ty = b % prm.tiles_y;
   b /= prm.tiles_y;
   const int zc0 = prm.z_lo + b * prm.zc, zc1 = min(zc0 + prm.zc, prm.z_hi);
-  // (the last tile of a row is anchored at the end of the row: it overlaps its neighbour -- the same values are stored
-  // twice -- and always holds the columns under the right band rows)
+  // (the last tile of a row is anchored at the end of the row: it overlaps its neighbour, which gives up the shared
+  // columns, and always holds the columns under the right band rows)
   const int x0 = min(tx * TX, max(0, prm.n2 - TX)), y0 = min(ty * G::TY, max(0, prm.n1 - G::TY));
   const bool edge_l = x0 == 0 && (prm.xb1.nl > 0 || prm.xb2.nl > 0), edge_r = x0 + TX >= prm.n2 && (prm.xb1.nr > 0 || prm.xb2.nr > 0);
   if ((edge_l | edge_r) && tid < 4 * kXBandMax * kXBandW) {
@@ -273,7 +273,15 @@ __global__ void __launch_bounds__(256, MINB) hessian3d_kernel(const __grid_const
 
   // own vector
   const int yo = y0 + wrp, xo = x0 + lane * V;
-  const bool own = yo >= prm.y_lo && yo < prm.y_hi && xo >= prm.x_lo && xo < prm.x_hi;
+  // columns / rows this tile stores (no point is stored twice).  Columns: natural tiles, except that the anchored last tile's
+  // share starts at or below the first right band column -- the band columns must all belong to the tile that evaluates
+  // them (fp64: with n2 % 64 == 2 and 3+ band columns the tile before the last one overlaps them and would store
+  // main-stencil values there); the left band stays with tile 0.  Rows: every tile runs the band rows it overlaps.
+  const int xsplit = min((prm.tiles_x - 1) * TX, (prm.n2 - max(prm.xb1.nr, prm.xb2.nr)) / V * V);
+  const bool xlast = tx + 1 == prm.tiles_x;
+  const int xown_lo = xlast && prm.tiles_x > 1 ? xsplit : x0, xown_hi = xlast ? prm.n2 : min((tx + 1) * TX, xsplit);
+  const int yown_hi = ty + 1 == prm.tiles_y ? prm.n1 : min((ty + 1) * G::TY, prm.n1 - G::TY);
+  const bool own = yo >= prm.y_lo && yo < min(prm.y_hi, yown_hi) && xo >= max(prm.x_lo, xown_lo) && xo < min(prm.x_hi, xown_hi);
   // a warp whose row is a boundary row of axis 1: band table (0 top, 1 bottom), row in it, staged row under its first column
   const int ybk = yo < prm.yb.nl ? 0 : (yo >= prm.n1 - prm.yb.nr && yo < prm.n1 ? 1 : -1);
   const int ybj = ybk == 0 ? yo : yo - (prm.n1 - prm.yb.nr);
@@ -765,7 +773,11 @@ __global__ void __launch_bounds__(128, MINB) hessian2d_kernel(const __grid_const
   const int strip = (int)(it % prm.strips), rest = (int)(it / prm.strips);
   const int x0 = min(strip * TX, max(0, prm.n1 - TX));
   const int xo = x0 + lane * V;
-  const bool own = xo < prm.n1;
+  // (natural strips, except that the anchored last strip's share starts at or below the first right band column: the band
+  // columns belong to the strip that evaluates them; the left band stays with strip 0)
+  const int xsplit = min((prm.strips - 1) * TX, (prm.n1 - max(prm.xb1.nr, prm.xb2.nr)) / V * V);
+  const bool xlast = strip + 1 == prm.strips;
+  const bool own = xo >= (xlast && prm.strips > 1 ? xsplit : x0) && xo < (xlast ? prm.n1 : min((strip + 1) * TX, xsplit));
   const bool edge_l = x0 == 0 && (prm.xb1.nl > 0 || prm.xb2.nl > 0), edge_r = x0 + TX >= prm.n1 && (prm.xb1.nr > 0 || prm.xb2.nr > 0);
   const int64_t N = (int64_t)prm.n0 * prm.n1;
 

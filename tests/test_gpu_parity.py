@@ -876,6 +876,25 @@ def test_fused_hessian2d_vs_oracle(dtype):
     assert ((h - h0).abs() / sc).max().item() <= 2e-5
 
 
+@pytest.mark.parametrize("n_last", [66, 130, 132, 260])
+def test_fused_hessians_last_tile_overlapping_the_right_band(n_last):
+    """fp64 strips are 64 columns wide: with n_last % 64 == 2 the tile before the anchored last tile overlaps the right band
+    columns (3-4 of them at accuracy 4-6).  They belong to the last tile alone; a regression here shows as main-stencil
+    values (zero-filled reads past the row) in one or two columns."""
+    rng = np.random.default_rng(n_last)
+    for acc in (4, 6):
+        x3 = rng.standard_normal((20, 21, n_last))
+        kw = dict(accuracy=acc, step_size=(0.1, 0.2, 0.3))
+        out = _call("hessian", x3, **kw)
+        assert _cabi.last_kernel() == "fused_hessian3d"
+        assert parity_error("hessian", x3, kw, out, O.hessian(x3, **kw)) <= TOL[np.dtype(np.float64)], (n_last, acc)
+        x2 = rng.standard_normal((40, n_last))
+        kw = dict(accuracy=acc, step_size=(0.1, 0.2))
+        out = _call("hessian", x2, **kw)
+        assert _cabi.last_kernel() == "fused_hessian2d"
+        assert parity_error("hessian", x2, kw, out, O.hessian(x2, **kw)) <= TOL[np.dtype(np.float64)], (n_last, acc)
+
+
 def test_fused_hessian3d_against_the_composition_on_a_big_grid():
     """Fused one-pass hessian == the 7-pass composition of axis kernels within the parity bound (the nesting order of the
     mixed entries differs, the boundary rows are the same dense rows), on a grid of several chunks and tiles; inf in the
