@@ -32,7 +32,7 @@ def main():
         x = torch.randn((n, n, n), device="cuda", dtype=dt)
         s = x.element_size()
         gb = 10 * s * n**3 / 1e9
-        for env in ({"FDX_HESS_DISABLE": "1"}, {}, {"FDX_HESS_MINB": "3"}, {"FDX_HESS_PLAIN_ST": "1"}):
+        for env in ({"FDX_HESS_DISABLE": "1"}, {}, {"FDX_HESS_ZC": "24"}, {"FDX_HESS_ZC": "48"}, {"FDX_HESS_ZC": "64"}):
             for k in ("FDX_HESS_DISABLE", "FDX_HESS_CPS", "FDX_HESS_ZC", "FDX_HESS_PART", "FDX_HESS_MINB", "FDX_HESS_PLAIN_ST", "FDX_HESS_XALIGN_B"):
                 os.environ.pop(k, None)
             os.environ.update(env)
